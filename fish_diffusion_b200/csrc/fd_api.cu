@@ -1,0 +1,145 @@
+// C-ABI entry points that build tap-GEMM descriptors (see include/fishdiff_b200.h for the contract).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "fd_common.cuh"
+#include "fd_host.h"
+
+namespace {
+thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void init_desc(FdTapGemm& p) { memset(&p, 0, sizeof(p)); p.acc_scale = 1.f; p.post_scale = 1.f; p.planes_scale = 1.f; }
+
+void set_src(FdTapGemm& p, int i, const uint16_t* ptr, int C) {
+  p.src[i] = ptr;
+  p.src_C[i] = C;
+  p.src_rs[i] = C;
+  p.src_bs[i] = (long long)p.T * C;
+  p.src_ps[i] = (long long)p.B * p.T * C;
+}
+
+int run(const FdTapGemm& p, int backend, cudaStream_t st) {
+  int rc;
+  if (backend == FD_BACKEND_TC) {
+    rc = fd_tapgemm_tc_launch(p, st);
+  } else if (backend == FD_BACKEND_SIMT) {
+    rc = fd_tapgemm_simt_launch(p, st);
+  } else {
+    fd_set_error("unknown backend %d", backend);
+    return -2;
+  }
+  if (rc == 0) fd_count_launch(1);
+  return rc;
+}
+}  // namespace
+
+void fd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" {
+
+void fd_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* fd_last_error(void) { return g_err; }
+int fd_abi_version(void) { return FD_ABI_VERSION; }
+long long fd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fd_tc_supported_linear(int n_total, int k_seg, int num_seg) {
+  FdTapGemm p;
+  init_desc(p);
+  p.B = 1; p.T = 128; p.n_total = n_total; p.num_seg = num_seg; p.k_total = k_seg * num_seg;
+  p.epi = FD_EPI_LINEAR;
+  if (num_seg < 1 || num_seg > FD_MAX_SEG) return 0;
+  for (int s = 0; s < num_seg; ++s) { p.seg[s].src = 0; p.seg[s].k_len = k_seg; }
+  set_src(p, 0, reinterpret_cast<const uint16_t*>(16), k_seg);
+  return fd_tapgemm_tc_supported(p);
+}
+
+int fd_wavenet_block_fwd(uint16_t* x_planes, const uint16_t* cond_planes, uint16_t* z_planes, const uint16_t* w1,
+                         const uint16_t* w2, const float* gb_full, const float* gb_lo, const float* gb_hi,
+                         int gb_bstride, const float* b2, float* skip_f32, uint16_t* skip_planes, float skip_scale,
+                         int B, int T, int C, int E, int dilation, int gate_tile, float w1_inv_scale,
+                         float w2_inv_scale, int flags, int prec, int backend, void* stream) {
+  FD_REQUIRE(B > 0 && T > 0 && C > 0 && E > 0 && dilation > 0, "fd_wavenet_block_fwd: bad shape");
+  FD_REQUIRE(C % 8 == 0 && E % 8 == 0, "fd_wavenet_block_fwd: C=%d, E=%d must be multiples of 8", C, E);
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- GEMM1: dilated conv (3 taps) + conditioner projection + gate
+  FdTapGemm p;
+  init_desc(p);
+  p.B = B; p.T = T; p.prec = prec;
+  p.n_total = 2 * C; p.k_total = 3 * C + E; p.num_seg = 4;
+  p.seg[0] = FdSeg{0, -dilation, 0, C};
+  p.seg[1] = FdSeg{0, 0, 0, C};
+  p.seg[2] = FdSeg{0, dilation, 0, C};
+  p.seg[3] = FdSeg{1, 0, 0, E};
+  set_src(p, 0, x_planes, C);
+  set_src(p, 1, cond_planes, E);
+  p.w = w1; p.acc_scale = w1_inv_scale;
+  p.epi = FD_EPI_GATE;
+  p.gbias_full = gb_full; p.gbias_lo = gb_lo; p.gbias_hi = gb_hi; p.gbias_bstride = gb_bstride;
+  p.dil = dilation; p.gate_tile = gate_tile; p.C = C;
+  p.out_planes = z_planes;
+  int rc = run(p, backend, st);
+  if (rc) return rc;
+  // ---- GEMM2: output projection + residual / skip
+  FdTapGemm q;
+  init_desc(q);
+  q.B = B; q.T = T; q.prec = prec;
+  q.n_total = 2 * C; q.k_total = C; q.num_seg = 1;
+  q.seg[0] = FdSeg{0, 0, 0, C};
+  set_src(q, 0, z_planes, C);
+  q.w = w2; q.acc_scale = w2_inv_scale;
+  q.epi = FD_EPI_RES_SKIP;
+  q.bias = b2; q.bias_bstride = 0;
+  q.x_planes = x_planes; q.skip_f32 = skip_f32; q.skip_planes = skip_planes; q.skip_scale = skip_scale;
+  q.first_layer = flags & 1; q.last_layer = (flags >> 1) & 1; q.C = C;
+  return run(q, backend, st);
+}
+
+int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream) {
+  FD_REQUIRE(d != nullptr, "fd_conv_cl_fwd: null descriptor");
+  FD_REQUIRE(d->ntaps >= 1 && d->ntaps <= FD_MAX_SEG, "fd_conv_cl_fwd: ntaps=%d out of range", d->ntaps);
+  FD_REQUIRE(d->B > 0 && d->T > 0 && d->Cin > 0 && d->N > 0, "fd_conv_cl_fwd: bad shape");
+  FdTapGemm p;
+  init_desc(p);
+  p.B = d->B; p.T = d->T; p.prec = d->prec;
+  p.n_total = d->N; p.k_total = d->ntaps * d->Cin; p.num_seg = d->ntaps;
+  for (int j = 0; j < d->ntaps; ++j) p.seg[j] = FdSeg{0, d->shifts[j], 0, d->Cin};
+  set_src(p, 0, d->in_planes, d->Cin);
+  p.w = d->w_planes; p.acc_scale = d->w_inv_scale;
+  p.epi = FD_EPI_LINEAR;
+  p.bias = d->bias; p.bias_bstride = 0;
+  p.addend = d->addend; p.res_f32 = d->res_f32; p.res_planes = d->res_planes;
+  p.post_scale = d->post_scale; p.out_f32 = d->out_f32; p.out_accum = d->out_accum;
+  p.out_planes = d->out_planes; p.planes_scale = d->planes_scale; p.act = d->act; p.act_slope = d->act_slope;
+  p.row_mask = d->row_mask;
+  return run(p, d->backend, (cudaStream_t)stream);
+}
+
+int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
+                    int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, int prec,
+                    int backend, void* stream) {
+  FD_REQUIRE(n_fft % 64 == 0 && hop % 8 == 0 && NB % 128 == 0, "fd_stft_mag_fwd: n_fft=%d hop=%d NB=%d unsupported",
+             n_fft, hop, NB);
+  const long long pitch = (Np + 7) / 8 * 8;
+  FD_REQUIRE((long long)(frames - 1) * hop + n_fft <= Np, "fd_stft_mag_fwd: frames exceed the padded signal");
+  FdTapGemm p;
+  init_desc(p);
+  p.B = B; p.T = frames; p.prec = prec;
+  p.n_total = 2 * NB; p.k_total = n_fft; p.num_seg = 1;
+  p.seg[0] = FdSeg{0, 0, 0, n_fft};
+  p.src[0] = padded; p.src_C[0] = n_fft;
+  p.src_rs[0] = hop; p.src_bs[0] = pitch; p.src_ps[0] = (long long)B * pitch;
+  p.w = dft_w; p.acc_scale = w_inv_scale;
+  p.epi = FD_EPI_MAG; p.gate_tile = 256; p.C = NB; p.mag_scale = mag_scale;
+  p.out_planes = mag_planes;
+  return run(p, backend, (cudaStream_t)stream);
+}
+
+}  // extern "C"

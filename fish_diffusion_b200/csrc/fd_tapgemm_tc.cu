@@ -1,0 +1,499 @@
+// tcgen05 / TMEM / TMA tap-GEMM for sm_100a.
+//
+//   D[b,t,n] = sum_seg sum_k  A_seg[b, t+shift_seg, c_off_seg+k] * W[n, koff_seg+k]
+//
+// A (activations) and W (packed weights) are stored as 16-bit split planes (see fd_common.cuh).
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B/64B/32B swizzle, OOB rows zero-filled:
+//                 that is how the conv zero padding and the time shift of each tap are realised)
+//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma kind::f16, 3 products per
+//                 k16 step: hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Pipelines: smem full/empty ring between TMA and MMA; 2 TMEM accumulator stages between MMA and
+// epilogue, so the epilogue of tile i overlaps the mainloop of tile i+1.
+#include <cuda.h>
+#include "fd_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand descriptor (see cute::UMMA::SmemDescriptor): start addr>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                          // LBO (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int W_BYTES_RAW = BLOCK_N * BLOCK_K * 2;
+  static constexpr int W_BYTES = (W_BYTES_RAW + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int TX_BYTES = 2 * A_BYTES + 2 * W_BYTES_RAW;
+  static constexpr int RAW_STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int NUM_STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS_RAW = ACC_STAGES * BLOCK_N;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int SWIZZLE_BYTES = BLOCK_K * 2;                       // 128 / 64 / 32
+  static constexpr uint32_t LAYOUT_TYPE = BLOCK_K == 64 ? 2u : BLOCK_K == 32 ? 4u : 6u;
+  static constexpr uint32_t SBO = 8 * SWIZZLE_BYTES;
+  static constexpr int BIAS_FLOATS = 3 * BLOCK_N;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + BIAS_FLOATS * 4 +
+                                    (2 * NUM_STAGES + 2 * ACC_STAGES) * 8 + 16;
+};
+
+template <int BLOCK_N, int BLOCK_K, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
+                     const __grid_constant__ CUtensorMap tm_w, const FdTapGemm p) {
+  using C = Cfg<BLOCK_N, BLOCK_K>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  float* bias_s = reinterpret_cast<float*>(smem + C::NUM_STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + C::BIAS_FLOATS);
+  uint64_t* empty_bar = full_bar + C::NUM_STAGES;
+  uint64_t* tfull_bar = empty_bar + C::NUM_STAGES;
+  uint64_t* tempty_bar = tfull_bar + C::ACC_STAGES;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + C::ACC_STAGES);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  const int tiles_t = (p.T + BLOCK_M - 1) / BLOCK_M;
+  const int num_m_tiles = p.B * tiles_t;
+  const int num_n_tiles = p.n_total / BLOCK_N;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_src0);
+    prefetch_tmap(&tm_src1);
+    prefetch_tmap(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+        const int b = m_tile / tiles_t, t0 = (m_tile % tiles_t) * BLOCK_M;
+        const int n0 = n_tile * BLOCK_N;
+        int koff = 0;
+        for (int s = 0; s < p.num_seg; ++s) {
+          const FdSeg sg = p.seg[s];
+          const CUtensorMap* tm = sg.src == 0 ? &tm_src0 : &tm_src1;
+          for (int k0 = 0; k0 < sg.k_len; k0 += BLOCK_K) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = stage_base + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], C::TX_BYTES);
+            tma_load_4d(st, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 0);
+            tma_load_4d(st + C::A_BYTES, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 1);
+            tma_load_3d(st + 2 * C::A_BYTES, &tm_w, &full_bar[stage], koff + k0, n0, 0);
+            tma_load_3d(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w, &full_bar[stage], koff + k0, n0, 1);
+            if (++stage == C::NUM_STAGES) { stage = 0; phase ^= 1; }
+          }
+          koff += sg.k_len;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t fmt = p.prec == FD_F16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      int total_k_blocks = 0;
+      for (int s = 0; s < p.num_seg; ++s) total_k_blocks += p.seg[s].k_len / BLOCK_K;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < total_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * C::STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_desc(st, C::SBO, C::LAYOUT_TYPE);
+          const uint64_t a_lo = make_kmajor_desc(st + C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
+          const uint64_t w_hi = make_kmajor_desc(st + 2 * C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
+          const uint64_t w_lo = make_kmajor_desc(st + 2 * C::A_BYTES + C::W_BYTES, C::SBO, C::LAYOUT_TYPE);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 elements * 2 B along K inside the swizzle row
+            // small terms first, the dominant hi*hi product last
+            umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+            umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =========================================================== epilogue
+    const int q = warp % 4;                 // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - EPI_WARP0 * 32;   // 0..127
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+      const int b = m_tile / tiles_t, t0 = (m_tile % tiles_t) * BLOCK_M;
+      const int n0 = n_tile * BLOCK_N;
+      const int t = t0 + row;
+      const bool valid = t < p.T;
+
+      // stage the per-column bias vectors of this tile in shared memory
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (EPI == FD_EPI_MAG) {
+        // no bias
+      } else if (EPI == FD_EPI_GATE) {
+        const size_t bo = (size_t)b * p.gbias_bstride + n0;
+        for (int i = etid; i < BLOCK_N; i += 128) {
+          bias_s[i] = p.gbias_full[bo + i];
+          bias_s[BLOCK_N + i] = p.gbias_lo[bo + i];
+          bias_s[2 * BLOCK_N + i] = p.gbias_hi[bo + i];
+        }
+      } else {
+        for (int i = etid; i < BLOCK_N; i += 128)
+          bias_s[i] = p.bias ? p.bias[(size_t)b * p.bias_bstride + n0 + i] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+
+      if (EPI == FD_EPI_GATE || EPI == FD_EPI_MAG) {
+        constexpr int HALF = BLOCK_N / 2;
+        for (int c = 0; c < HALF; c += 16) {
+          float g[16], f[16];
+          tmem_ld16(taddr + c, g);
+          tmem_ld16(taddr + HALF + c, f);
+          if (valid) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float g8[8], f8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { g8[i] = g[h * 8 + i]; f8[i] = f[h * 8 + i]; }
+              const int cc = c + h * 8;
+              if (EPI == FD_EPI_MAG)
+                fd_epi_mag<8>(p, b, t, n_tile * HALF + cc, g8, f8);
+              else
+                fd_epi_gate<8>(p, b, t, n_tile * HALF + cc, g8, f8, bias_s + cc, bias_s + HALF + cc,
+                               bias_s + BLOCK_N + cc, bias_s + BLOCK_N + HALF + cc, bias_s + 2 * BLOCK_N + cc,
+                               bias_s + 2 * BLOCK_N + HALF + cc);
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          if (valid) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float v8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = v[h * 8 + i];
+              const int cc = c + h * 8;
+              if (EPI == FD_EPI_LINEAR) fd_epi_linear<8>(p, b, t, n0 + cc, v8, bias_s, n0);
+              else fd_epi_res_skip<8>(p, b, t, n0 + cc, v8, bias_s + cc);
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int block_k) {
+  return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int make_src_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, long long rs, long long bs,
+                 long long ps, int block_k) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)bs * 2, (cuuint64_t)ps * 2};
+  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)BLOCK_M, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(src) failed: %d (B=%d T=%d C=%d bk=%d ptr=%p)", (int)r, B,
+             T, C, block_k, (const void*)ptr);
+  return 0;
+}
+
+int make_w_map(CUtensorMap* m, const uint16_t* ptr, int N, int K, int block_n, int block_k) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)block_n, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(w) failed: %d (N=%d K=%d bn=%d bk=%d)", (int)r, N, K,
+             block_n, block_k);
+  return 0;
+}
+
+int g_num_sms = 0;
+
+template <int BLOCK_N, int BLOCK_K, int EPI>
+int launch_cfg(const FdTapGemm& p, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, BLOCK_K>;
+  CUtensorMap tm0, tm1, tmw;
+  int rc = make_src_map(&tm0, p.src[0], p.B, p.T, p.src_C[0], p.src_rs[0], p.src_bs[0], p.src_ps[0], BLOCK_K);
+  if (rc) return rc;
+  if (p.src[1] != nullptr) {
+    rc = make_src_map(&tm1, p.src[1], p.B, p.T, p.src_C[1], p.src_rs[1], p.src_bs[1], p.src_ps[1], BLOCK_K);
+    if (rc) return rc;
+  } else {
+    tm1 = tm0;
+  }
+  rc = make_w_map(&tmw, p.w, p.n_total, p.k_total, BLOCK_N, BLOCK_K);
+  if (rc) return rc;
+
+  auto kern = fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    FD_CHECK_CUDA(cudaGetDevice(&dev));
+    FD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles_t = (p.T + BLOCK_M - 1) / BLOCK_M;
+  const int num_tiles = p.B * tiles_t * (p.n_total / BLOCK_N);
+  const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tmw, p);
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+int launch_epi(const FdTapGemm& p, cudaStream_t stream) {
+  if (p.epi == FD_EPI_GATE) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_GATE>(p, stream);
+  if (p.epi == FD_EPI_MAG) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_MAG>(p, stream);
+  if (p.epi == FD_EPI_RES_SKIP) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_RES_SKIP>(p, stream);
+  return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_LINEAR>(p, stream);
+}
+
+// choose (BLOCK_N, BLOCK_K) for a problem; bn = 0 if no tensor-core instantiation fits
+void pick_cfg(const FdTapGemm& p, int* bn, int* bk) {
+  *bn = 0; *bk = 0;
+  bool all64 = true, all32 = true, all16 = true;
+  for (int s = 0; s < p.num_seg; ++s) {
+    if (p.seg[s].c_off % 16 != 0) return;
+    all64 &= p.seg[s].k_len % 64 == 0;
+    all32 &= p.seg[s].k_len % 32 == 0;
+    all16 &= p.seg[s].k_len % 16 == 0;
+  }
+  const int k = all64 ? 64 : all32 ? 32 : all16 ? 16 : 0;
+  if (k == 0) return;
+  if (p.epi == FD_EPI_GATE || p.epi == FD_EPI_MAG) {
+    const int n = p.gate_tile;
+    if ((n != 256 && n != 128) || p.n_total % n != 0 || k != 64) return;
+    *bn = n; *bk = 64;
+    return;
+  }
+  int n = 256;
+  while (n >= 16 && (p.n_total % n != 0 || (p.epi == FD_EPI_RES_SKIP && p.C % n != 0))) n >>= 1;
+  if (n < 16) return;
+  if (k == 64) {
+    if (n < 64) return;
+    *bn = n; *bk = 64;
+  } else if (k == 32) {
+    if (p.epi != FD_EPI_LINEAR || n < 32) return;
+    *bn = n > 64 ? 64 : n; *bk = 32;
+  } else {
+    if (p.epi != FD_EPI_LINEAR) return;
+    *bn = n > 32 ? 32 : n; *bk = 16;
+  }
+}
+
+}  // namespace
+
+int fd_tapgemm_tc_supported(const FdTapGemm& p) {
+  int bn, bk;
+  pick_cfg(p, &bn, &bk);
+  if (bn == 0) return 0;
+  for (int s = 0; s < 2; ++s)
+    if (p.src[s] != nullptr && (p.src_rs[s] % 8 != 0 || p.src_bs[s] % 8 != 0 || p.src_ps[s] % 8 != 0)) return 0;
+  if (p.k_total % 8 != 0) return 0;
+  return 1;
+}
+
+int fd_tapgemm_tc_launch(const FdTapGemm& p, cudaStream_t stream) {
+  int bn, bk;
+  pick_cfg(p, &bn, &bk);
+  FD_REQUIRE(bn != 0 && fd_tapgemm_tc_supported(p),
+             "tapgemm(tc): no tensor-core instantiation for n_total=%d k_total=%d epi=%d", p.n_total, p.k_total,
+             p.epi);
+  if (bk == 64) {
+    if (bn == 256) return launch_epi<256, 64>(p, stream);
+    if (bn == 128) return launch_epi<128, 64>(p, stream);
+    if (p.epi == FD_EPI_RES_SKIP) return launch_cfg<64, 64, FD_EPI_RES_SKIP>(p, stream);
+    return launch_cfg<64, 64, FD_EPI_LINEAR>(p, stream);
+  }
+  if (bk == 32) {
+    FD_REQUIRE(p.epi == FD_EPI_LINEAR, "tapgemm(tc): BLOCK_K=32 only instantiated for the linear epilogue");
+    if (bn == 64) return launch_cfg<64, 32, FD_EPI_LINEAR>(p, stream);
+    return launch_cfg<32, 32, FD_EPI_LINEAR>(p, stream);
+  }
+  FD_REQUIRE(p.epi == FD_EPI_LINEAR, "tapgemm(tc): BLOCK_K=16 only instantiated for the linear epilogue");
+  if (bn == 32) return launch_cfg<32, 16, FD_EPI_LINEAR>(p, stream);
+  return launch_cfg<16, 16, FD_EPI_LINEAR>(p, stream);
+}

@@ -1,0 +1,166 @@
+/* fishdiff_b200.h -- C ABI of the B200-native fish-diffusion hot path (libfishdiff_b200.so).
+ *
+ * The reference (fishaudio/fish-diffusion @ 8e8f8cd) contains no native code: its
+ * hot path is PyTorch library dispatch.  This library is what a maintainer binds (ctypes, see
+ * INTEGRATION.md) behind the reference's own Python classes; each entry point cites the reference
+ * computation it replaces.  Conventions:
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless named host_*;
+ *   - the caller owns every buffer including workspaces; functions never allocate and never synchronise;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, negative on error; fd_last_error() returns the message (thread-local);
+ *   - activations are channels-last "split planes" (fd_common.cuh): uint16 planes[2][B][T][C],
+ *     value = hi + lo, `prec` = FD_PREC_F16 (22-bit mantissa) or FD_PREC_BF16 (16-bit mantissa);
+ *   - `backend`: FD_BACKEND_TC = tcgen05/TMEM/TMA tensor-core kernel (sm_100a),
+ *                FD_BACKEND_SIMT = fp32 CUDA-core twin (device-side checker / uncovered shapes).
+ *     There is no CPU path in this library.
+ */
+#ifndef FISHDIFF_B200_H
+#define FISHDIFF_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_PREC_F16 0
+#define FD_PREC_BF16 1
+#define FD_BACKEND_TC 0
+#define FD_BACKEND_SIMT 1
+#define FD_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------- misc */
+int fd_abi_version(void);
+const char* fd_last_error(void);
+/* number of kernel launches issued by this library since process start (bench.py "gpu_launches") */
+long long fd_launch_count(void);
+/* 1 if tensor-core instantiation exists for the given linear tap-GEMM shape */
+int fd_tc_supported_linear(int n_total, int k_seg, int num_seg);
+
+/* ------------------------------------------------------------------------------ layout / packing */
+/* fp32 [B,C,T] (reference NCW layout, wavenet.py:194 `x: [B, M, T]`) -> split planes [2][B][T][C];
+ * rows with mask[b,t]!=0 are zeroed (wavenet.py:217-221 masked_fill). mask may be NULL. */
+int fd_split_ncw(const float* src, const uint8_t* mask, uint16_t* planes, int B, int C, int T, int prec,
+                 void* stream);
+/* fp32 [B,T,C] channels-last -> split planes; value*scale; optional row mask */
+int fd_split_nwc(const float* src, const uint8_t* mask, uint16_t* planes, int B, int T, int C, float scale,
+                 int prec, void* stream);
+/* fp32 [B,T,C] -> fp32 [B,C,T] and back (boundary transposes of the drop-in WaveNet.forward) */
+int fd_transpose_nwc_to_ncw(const float* src, float* dst, int B, int T, int C, void* stream);
+int fd_transpose_ncw_to_nwc(const float* src, float* dst, int B, int C, int T, void* stream);
+/* fp32 weight matrix [N][K] -> split planes [2][N][K] of (w*scale) */
+int fd_pack_weight(const float* w, uint16_t* planes, long long n_elems, float scale, int prec, void* stream);
+
+/* ------------------------------------------------------------------------- WaveNet denoiser (a10-a12) */
+/* DiffusionEmbedding + mlp (wavenet.py:13-27,170-174,214-215): steps[Bs] (float; int steps are cast by
+ * the caller exactly like `x[:, None] * emb`) -> s[Bs][C].
+ * w0 [4C][C], b0 [4C] (may be NULL), w1 [C][4C], b1 [C] (may be NULL); ws: workspace Bs*5C floats. */
+int fd_wavenet_step_mlp(const float* steps, const float* w0, const float* b0, const float* w1, const float* b1,
+                        float* s_out, float* ws, int Bs, int C, void* stream);
+/* Per-layer diffusion_projection (wavenet.py:107) folded into the gate bias of the fused block:
+ *   d_l = Wd[l] s + bd[l];  full = bias_sum[l] + sum_tap W1p[l][:, tap*C:(tap+1)*C] d_l ; lo/hi = tap 0 / tap 2 term.
+ * wd [L][C][C], bd [L][C] or NULL, w1p fp32 packed [L][2C][KT] (KT = 3C+E), bias_sum [L][2C] packed order.
+ * outputs gb_full/gb_lo/gb_hi [L][Bs][2C]; ws: L*Bs*C floats. */
+int fd_wavenet_gate_bias(const float* s, const float* wd, const float* bd, const float* w1p, const float* bias_sum,
+                         float* gb_full, float* gb_lo, float* gb_hi, float* ws, int L, int Bs, int C, int KT,
+                         void* stream);
+/* One ResidualBlock.forward (wavenet.py:106-120), fused as two tap-GEMM launches:
+ *   GEMM1  y = [W_conv(3 taps) | W_cond] . [x(t-d), x(t), x(t+d), cond(t)] + gate bias ; z = sigmoid(y_g)*tanh(y_f)
+ *   GEMM2  o = W_out z + b ;  x <- (x + o_res)/sqrt(2) (in place) ;  skip_acc (+)= o_skip
+ * x_planes [2][B][T][C] in/out, cond_planes [2][B][T][E], z_planes workspace [2][B][T][C],
+ * w1 planes [2][2C][3C+E] (gate/filter rows interleaved per `gate_tile`), w2 planes [2][2C][C],
+ * gb_* [Bs][2C] for this layer (gb_bstride = 2C if per-item steps else 0), b2 [2C],
+ * skip_f32 [B][T][C] accumulator; flags bit0 = first layer (skip written, not accumulated),
+ * bit1 = last layer (skip_planes <- split((skip_f32 + o_skip) * skip_scale), x not updated). */
+int fd_wavenet_block_fwd(uint16_t* x_planes, const uint16_t* cond_planes, uint16_t* z_planes,
+                         const uint16_t* w1, const uint16_t* w2, const float* gb_full, const float* gb_lo,
+                         const float* gb_hi, int gb_bstride, const float* b2, float* skip_f32,
+                         uint16_t* skip_planes, float skip_scale, int B, int T, int C, int E, int dilation,
+                         int gate_tile, float w1_inv_scale, float w2_inv_scale, int flags, int prec, int backend,
+                         void* stream);
+
+/* --------------------------------------------------------------- generic channels-last conv / linear */
+/* out[b,t,n] = post( sum_j sum_c in[b, t + shifts[j], c] * w[n, j*Cin + c] * w_inv_scale + bias[n]
+ *                    + addend[b,t,n] + res ) ; see FdTapGemm in csrc/fd_common.cuh for the exact epilogue.
+ * Used for: WaveNet input/skip/output projections (wavenet.py:211-212,229-231), NSF-HiFiGAN conv_pre,
+ * ResBlock1 convs (models.py:103-110), polyphase ConvTranspose1d (models.py:421), mel filterbank. */
+typedef struct fd_conv_desc {
+  const uint16_t* in_planes; /* [2][B][T][Cin] */
+  const uint16_t* w_planes;  /* [2][N][ntaps*Cin] */
+  const float* bias;         /* [N] or NULL */
+  const float* addend;       /* fp32 [B][T][N] or NULL */
+  const float* res_f32;      /* fp32 [B][T][N] or NULL */
+  const uint16_t* res_planes;/* [2][B][T][N] or NULL */
+  const uint8_t* row_mask;   /* [B][T] or NULL */
+  float* out_f32;            /* [B][T][N] or NULL */
+  uint16_t* out_planes;      /* [2][B][T][N] or NULL */
+  int B, T, Cin, N;
+  int ntaps;
+  int shifts[16];
+  float w_inv_scale, post_scale, planes_scale, act_slope;
+  int out_accum;             /* out_f32 += */
+  int act;                   /* 0 none, 1 relu, 2 leaky-relu(act_slope): applied to the planes output only */
+  int prec, backend;
+} fd_conv_desc;
+int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------- sampler (a5-a9, K10-K12) */
+/* NaiveNoisePredictor.forward (noise_predictor.py:73-104):
+ *   x0 = c_recip*x - c_recipm1*eps ; clamp ; mean = c1*x0 + c2*x ; x' = mean + sigma*noise
+ * sigma = [t>0]*exp(0.5*logvar_t) computed by the caller from the bit-exact tables.
+ * noise: injected N(0,1) tensor or NULL -> in-kernel Philox4x32-10 (seed, offset).
+ * writes x_out (fp32, may alias x) and optionally split planes of x' for the next denoiser call. */
+int fd_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, uint16_t* x_planes,
+                 long long n, float c_recip, float c_recipm1, float c1, float c2, float sigma, float clip_min,
+                 float clip_max, unsigned long long seed, unsigned long long offset, int prec, void* stream);
+/* out = sum_i coef[i] * in[i]  (PLMS noise_predictor.py:118-148, UniPC uni_pc.py:664-680 updates);
+ * nterms <= 6; optionally also writes split planes. in[i] may alias out. */
+int fd_lincomb(float* out, uint16_t* out_planes, const float* const* host_in_ptrs, const float* host_coefs,
+               int nterms, long long n, int prec, void* stream);
+/* y = x*scale[c] + shift[c] over channels-last [rows][C] (norm_spec/denorm_spec diffusion.py:315-319);
+ * scale/shift have length C or 1 (nparam). */
+int fd_affine_cl(const float* x, float* y, const float* scale, const float* shift, int nparam, long long rows,
+                 int C, void* stream);
+/* q_sample (diffusion.py:120-127): y = a[b]*x + s[b]*noise, a/s per batch item (device arrays [B]) */
+int fd_q_sample(const float* x, const float* noise, const float* a, const float* s, float* y, int B,
+                long long per_item, void* stream);
+/* fill with N(0,1) from Philox4x32-10 */
+int fd_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream);
+
+/* --------------------------------------------------------------- NSF-HiFiGAN source module (a15) */
+/* Generator.forward f0 upsample + SourceModuleHnNSF (models.py:411-415, 201-294, 337-350):
+ * f0 [B][T] frames -> har [B][T*hop] (fp32).  9 harmonics, phase accumulated exactly (64-bit fixed
+ * point scan), sine_amp 0.1, noise_std 0.003.  lin_w[H], lin_b[1] = m_source.l_linear.
+ * rand_ini [B][H] (rand_ini[:,0] must be 0) ; noise [B][S][H] injected N(0,1) or NULL -> Philox.
+ * ws: workspace, fd_sinegen_ws_bytes(B, T*hop) bytes. */
+size_t fd_sinegen_ws_bytes(int B, long long S);
+int fd_sinegen_fwd(const float* f0, const float* lin_w, const float* lin_b, const float* rand_ini,
+                   const float* noise, float* har, void* ws, int B, int T, int hop, int H, float sampling_rate,
+                   float sine_amp, float noise_std, unsigned long long seed, void* stream);
+/* noise_convs[i] (models.py:380-393,422): Conv1d(1 -> C, kernel k, stride s, padding p) over har [B][S]
+ * -> fp32 channels-last [B][S_out][C],  S_out = (S + 2p - k)/s + 1 */
+int fd_source_conv_fwd(const float* har, const float* w /*[C][k]*/, const float* bias /*[C]*/, float* out,
+                       int B, long long S, int C, int k, int s, int p, void* stream);
+/* conv_post + tanh (models.py:434-436): in planes [2][B][S][C] (already leaky-relu'd by the producer)
+ * -> wav [B][S];  w [k][C], bias[1] */
+int fd_conv_post_fwd(const uint16_t* in_planes, const float* w, const float* bias, float* wav, int B,
+                     long long S, int C, int k, int prec, void* stream);
+
+/* ------------------------------------------------------------------------ mel front end (a19-a20) */
+/* reflect-pad + split: wav [B][N] -> planes [2][B][Np] with Np = N + 2*pad (pitch_adjustable_mel.py:61-69) */
+int fd_reflect_pad_split(const float* wav, uint16_t* planes, int B, long long N, int pad, int prec, void* stream);
+/* framed DFT magnitude as a tap-GEMM over overlapping frames (pitch_adjustable_mel.py:71-83):
+ * padded planes [2][B][Np], frames = (Np - n_fft)/hop + 1, dft_w planes [2][2*NB][n_fft] (window folded in,
+ * rows interleaved re/im per 256-column tile, NB = padded bin count, multiple of 128)
+ * -> mag planes [2][B][frames][NB] of sqrt(re^2+im^2+1e-9)*mag_scale */
+int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
+                    int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, int prec,
+                    int backend, void* stream);
+/* log(clamp(x, clip)) * out_scale over fp32 (audio.py:11-18 dynamic_range_compression) */
+int fd_log_clamp(const float* x, float* y, long long n, float clip, float out_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISHDIFF_B200_H */
