@@ -1,0 +1,197 @@
+"""ctypes binding of libfishdiff_b200.so (the C ABI declared in include/fishdiff_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails this module raises.  PyTorch is used by the
+callers only for device memory and streams; raw device pointers are passed down.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ubyte, c_ulonglong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfishdiff_b200.so")
+
+PREC_F16, PREC_BF16 = 0, 1
+BACKEND_TC, BACKEND_SIMT = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+ABI_VERSION = 1
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """struct fd_conv_desc (include/fishdiff_b200.h)."""
+    _fields_ = [
+        ("in_planes", c_void_p), ("w_planes", c_void_p), ("bias", c_void_p), ("addend", c_void_p),
+        ("res_f32", c_void_p), ("res_planes", c_void_p), ("row_mask", c_void_p), ("out_f32", c_void_p),
+        ("out_planes", c_void_p),
+        ("B", c_int), ("T", c_int), ("Cin", c_int), ("N", c_int), ("ntaps", c_int), ("shifts", c_int * 16),
+        ("w_inv_scale", c_float), ("post_scale", c_float), ("planes_scale", c_float), ("act_slope", c_float),
+        ("out_accum", c_int), ("act", c_int), ("prec", c_int), ("backend", c_int),
+    ]
+
+
+_SIGS = {
+    "fd_abi_version": (c_int, []),
+    "fd_last_error": (c_char_p, []),
+    "fd_launch_count": (c_longlong, []),
+    "fd_tc_supported_linear": (c_int, [c_int, c_int, c_int]),
+    "fd_split_ncw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "fd_split_nwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "fd_transpose_nwc_to_ncw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fd_transpose_ncw_to_nwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fd_pack_weight": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_int, c_void_p]),
+    "fd_wavenet_step_mlp": (c_int, [c_void_p] * 7 + [c_int, c_int, c_void_p]),
+    "fd_wavenet_gate_bias": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "fd_wavenet_block_fwd": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 +
+                             [c_float, c_float, c_int, c_int, c_int, c_void_p]),
+    "fd_conv_cl_fwd": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "fd_ddpm_step": (c_int, [c_void_p] * 5 + [c_longlong] + [c_float] * 7 + [c_ulonglong, c_ulonglong, c_int, c_void_p]),
+    "fd_lincomb": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p]),
+    "fd_affine_cl": (c_int, [c_void_p] * 4 + [c_int, c_longlong, c_int, c_void_p]),
+    "fd_q_sample": (c_int, [c_void_p] * 5 + [c_int, c_longlong, c_void_p]),
+    "fd_randn": (c_int, [c_void_p, c_longlong, c_ulonglong, c_ulonglong, c_void_p]),
+    "fd_sinegen_ws_bytes": (c_size_t, [c_int, c_longlong]),
+    "fd_sinegen_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_ulonglong,
+                                                c_void_p]),
+    "fd_source_conv_fwd": (c_int, [c_void_p] * 4 + [c_int, c_longlong, c_int, c_int, c_int, c_int, c_void_p]),
+    "fd_conv_post_fwd": (c_int, [c_void_p] * 4 + [c_int, c_longlong, c_int, c_int, c_int, c_void_p]),
+    "fd_reflect_pad_split": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]),
+    "fd_stft_mag_fwd": (c_int, [c_void_p] * 3 + [c_int, c_longlong, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                                                 c_int, c_void_p]),
+    "fd_log_clamp": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_float, c_void_p]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises NativeError if it is missing -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  fish_diffusion_b200 has no CPU or PyTorch fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if l.fd_abi_version() != ABI_VERSION:
+            raise NativeError(f"ABI mismatch: library {l.fd_abi_version()} != binding {ABI_VERSION}")
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().fd_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise NativeError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "native kernels need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise NativeError(f"{name} is on {t.device}: fish_diffusion_b200 runs on CUDA (sm_100a) only, there is no CPU path")
+
+
+def launch_count() -> int:
+    return int(lib().fd_launch_count())
+
+
+def prec_code(precision: str) -> int:
+    p = precision.lower()
+    if p in ("f16", "fp16", "half"):
+        return PREC_F16
+    if p in ("bf16", "bfloat16"):
+        return PREC_BF16
+    raise ValueError(f"unknown precision {precision!r} (use 'f16' or 'bf16')")
+
+
+def backend_code(backend: str) -> int:
+    b = backend.lower()
+    if b in ("tc", "tcgen05"):
+        return BACKEND_TC
+    if b in ("simt", "fp32"):
+        return BACKEND_SIMT
+    raise ValueError(f"unknown backend {backend!r} (use 'tc' or 'simt')")
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def pow2_scale(w: torch.Tensor, target: float = 64.0) -> float:
+    """Power-of-two prescale s such that max|w*s| lies in [target/2, target): keeps the fp16 lo-plane of the
+    packed weights out of the subnormal range; undone exactly by the kernel's acc_scale = 1/s."""
+    m = float(w.detach().abs().max())
+    if m == 0.0 or not (m == m):
+        return 1.0
+    import math
+    return float(2.0 ** math.floor(math.log2(target / m)))
+
+
+def pack_weight(w2d: torch.Tensor, prec: int, scale: float) -> torch.Tensor:
+    """fp32 [N, K] (device) -> split planes uint16 [2, N, K]."""
+    w2d = w2d.detach().to(torch.float32).contiguous()
+    require_cuda(w2d, "weight")
+    out = torch.empty((2,) + tuple(w2d.shape), dtype=torch.int16, device=w2d.device)
+    check(lib().fd_pack_weight(ptr(w2d), ptr(out), w2d.numel(), scale, prec, stream_ptr(w2d.device)), "fd_pack_weight")
+    return out
+
+
+def split_nwc(x: torch.Tensor, prec: int, mask=None, scale: float = 1.0, out=None) -> torch.Tensor:
+    """fp32 [B,T,C] -> planes [2,B,T,C]."""
+    B, T, C = x.shape
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((2, B, T, C), dtype=torch.int16, device=x.device)
+    check(lib().fd_split_nwc(ptr(x), ptr(mask), ptr(out), B, T, C, scale, prec, stream_ptr(x.device)), "fd_split_nwc")
+    return out
+
+
+def split_ncw(x: torch.Tensor, prec: int, mask=None, out=None) -> torch.Tensor:
+    """fp32 [B,C,T] -> planes [2,B,T,C]."""
+    B, C, T = x.shape
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((2, B, T, C), dtype=torch.int16, device=x.device)
+    check(lib().fd_split_ncw(ptr(x), ptr(mask), ptr(out), B, C, T, prec, stream_ptr(x.device)), "fd_split_ncw")
+    return out
+
+
+def conv_cl(in_planes, w_planes, B, T, Cin, N, shifts, *, bias=None, addend=None, res_f32=None, res_planes=None,
+            row_mask=None, out_f32=None, out_planes=None, w_inv_scale=1.0, post_scale=1.0, planes_scale=1.0,
+            act=ACT_NONE, act_slope=0.0, out_accum=False, prec=PREC_F16, backend=BACKEND_TC):
+    d = ConvDesc()
+    d.in_planes, d.w_planes = ptr(in_planes), ptr(w_planes)
+    d.bias, d.addend, d.res_f32, d.res_planes = ptr(bias), ptr(addend), ptr(res_f32), ptr(res_planes)
+    d.row_mask, d.out_f32, d.out_planes = ptr(row_mask), ptr(out_f32), ptr(out_planes)
+    d.B, d.T, d.Cin, d.N, d.ntaps = B, T, Cin, N, len(shifts)
+    for i, s in enumerate(shifts):
+        d.shifts[i] = int(s)
+    d.w_inv_scale, d.post_scale, d.planes_scale, d.act_slope = w_inv_scale, post_scale, planes_scale, act_slope
+    d.out_accum, d.act, d.prec, d.backend = int(out_accum), act, prec, backend
+    check(lib().fd_conv_cl_fwd(ctypes.byref(d), stream_ptr(in_planes.device)), "fd_conv_cl_fwd")
+
+
+def tc_supported_linear(n_total: int, k_seg: int, num_seg: int) -> bool:
+    return bool(lib().fd_tc_supported_linear(n_total, k_seg, num_seg))

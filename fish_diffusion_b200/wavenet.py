@@ -1,0 +1,275 @@
+"""B200-native WaveNet denoiser: drop-in for the reference ``fish_diffusion/modules/wavenet.py``.
+
+Same constructor arguments, same ``state_dict`` keys and the same ``forward`` contract as the reference class
+(wavenet.py:157-236), registered as ``DENOISERS["WaveNetDenoiser"]``.  The arithmetic runs in
+the hand-written sm_100a kernels of libfishdiff_b200.so; there is no PyTorch/CPU fallback.
+
+Data flow of one call (all activations channels-last split planes, see csrc/fd_common.cuh):
+  step mlp (3 tiny kernels) -> gate-bias tables (2 kernels) -> head tap-GEMM (input_projection + ReLU + mask)
+  -> L x [GEMM1: dilated conv + conditioner + gate | GEMM2: output projection + residual/skip]
+  -> tail tap-GEMMs (skip_projection + ReLU, output_projection + mask).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+from torch import nn
+
+from . import _native as N
+from .registry import DENOISERS
+
+
+class Mish(nn.Module):
+    """Parameter-free placeholder so that ``mlp`` keeps the reference indices 0/2 (wavenet.py:8-10,170-174)."""
+
+    def forward(self, x):  # pragma: no cover - never executed: the MLP runs in fd_wavenet_step_mlp
+        raise RuntimeError("fish_diffusion_b200.WaveNet runs its MLP natively")
+
+
+class DiffusionEmbedding(nn.Module):
+    def __init__(self, d_denoiser):
+        super().__init__()
+        self.dim = d_denoiser
+
+
+class LinearNorm(nn.Module):
+    """Parameter holder with the reference's key names and initialiser (wavenet.py:30-43)."""
+
+    def __init__(self, in_features, out_features, bias=False):
+        super().__init__()
+        self.linear = nn.Linear(in_features, out_features, bias)
+        nn.init.xavier_uniform_(self.linear.weight)
+        if bias:
+            nn.init.constant_(self.linear.bias, 0.0)
+
+
+class ConvNorm(nn.Module):
+    """Parameter holder with the reference's key names and initialiser (wavenet.py:46-80)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=None, dilation=1, bias=True):
+        super().__init__()
+        if padding is None:
+            assert kernel_size % 2 == 1
+            padding = int(dilation * (kernel_size - 1) / 2)
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding,
+                              dilation=dilation, bias=bias)
+        nn.init.kaiming_normal_(self.conv.weight)
+
+
+class ResidualBlock(nn.Module):
+    """Parameter holder for one block (wavenet.py:83-104); computed by fd_wavenet_block_fwd."""
+
+    def __init__(self, d_encoder, residual_channels, use_linear_bias=False, dilation=1):
+        super().__init__()
+        self.dilation = dilation
+        self.conv_layer = ConvNorm(residual_channels, 2 * residual_channels, kernel_size=3, stride=1,
+                                   padding=dilation, dilation=dilation)
+        self.diffusion_projection = LinearNorm(residual_channels, residual_channels, use_linear_bias)
+        self.conditioner_projection = ConvNorm(d_encoder, 2 * residual_channels, kernel_size=1)
+        self.output_projection = ConvNorm(residual_channels, 2 * residual_channels, kernel_size=1)
+
+
+def _gate_half(C: int) -> int:
+    for g in (128, 64, 16):
+        if C % g == 0:
+            return g
+    raise ValueError(f"residual_channels={C} must be a multiple of 16")
+
+
+class WaveNet(nn.Module):
+    """WaveNet denoiser (reference wavenet.py:151-236) on sm_100a kernels.
+
+    Extra keyword arguments (not in the reference, defaults keep reference configs working):
+      precision: "f16" (22-bit split planes, fp32-faithful) or "bf16" (16-bit split planes, fp32 range)
+      backend:   "auto" (tcgen05 when the shape has a tensor-core instantiation, else the SIMT twin), "tc", "simt"
+    """
+
+    def __init__(self, mel_channels=128, d_encoder=256, residual_channels=512, residual_layers=20,
+                 use_linear_bias=False, dilation_cycle=None, precision="f16", backend="auto"):
+        super().__init__()
+        self.mel_channels, self.d_encoder = mel_channels, d_encoder
+        self.residual_channels, self.n_layers = residual_channels, residual_layers
+        self.input_projection = ConvNorm(mel_channels, residual_channels, kernel_size=1)
+        self.diffusion_embedding = DiffusionEmbedding(residual_channels)
+        self.mlp = nn.Sequential(
+            LinearNorm(residual_channels, residual_channels * 4, use_linear_bias),
+            Mish(),
+            LinearNorm(residual_channels * 4, residual_channels, use_linear_bias),
+        )
+        self.residual_layers = nn.ModuleList([
+            ResidualBlock(d_encoder, residual_channels, use_linear_bias=use_linear_bias,
+                          dilation=2 ** (i % dilation_cycle) if dilation_cycle else 1)
+            for i in range(residual_layers)
+        ])
+        self.skip_projection = ConvNorm(residual_channels, residual_channels, kernel_size=1)
+        self.output_projection = ConvNorm(residual_channels, mel_channels, kernel_size=1)
+        nn.init.zeros_(self.output_projection.conv.weight)   # wavenet.py:192
+
+        self.precision = precision
+        self.backend = os.environ.get("FD_BACKEND", backend)
+        self._pack = None
+        self._pack_key = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------------------------ packing
+    def _resolve_backend(self) -> int:
+        if self.backend != "auto":
+            return N.backend_code(self.backend)
+        C, E, M = self.residual_channels, self.d_encoder, self.mel_channels
+        ok = (C % 64 == 0 and E % 64 == 0 and M % 64 == 0 and _gate_half(C) in (128, 64))
+        return N.BACKEND_TC if ok else N.BACKEND_SIMT
+
+    def _packed(self, device):
+        key = (str(device), self.precision, tuple(p._version for p in self.parameters()),
+               tuple(p.data_ptr() for p in self.parameters()))
+        if self._pack is not None and self._pack_key == key:
+            return self._pack
+        prec = N.prec_code(self.precision)
+        C, E, M, L = self.residual_channels, self.d_encoder, self.mel_channels, self.n_layers
+        half = _gate_half(C)
+        gate_tile = 2 * half
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32)
+        # gate/filter row interleave per column tile: tile q holds gates [q*half,(q+1)*half) then their filters
+        idx = torch.arange(C, device=device).view(C // half, half)
+        perm = torch.cat([idx, idx + C], dim=1).reshape(-1)
+
+        def pack(w2d):
+            s = N.pow2_scale(w2d)
+            return N.pack_weight(w2d, prec, s), 1.0 / s
+
+        pk = {"prec": prec, "gate_tile": gate_tile, "backend": self._resolve_backend()}
+        pk["w_in"], pk["w_in_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0])
+        pk["b_in"] = f32(self.input_projection.conv.bias).contiguous()
+        pk["mlp_w0"] = f32(self.mlp[0].linear.weight).contiguous()
+        pk["mlp_b0"] = f32(self.mlp[0].linear.bias).contiguous() if self.mlp[0].linear.bias is not None else None
+        pk["mlp_w1"] = f32(self.mlp[2].linear.weight).contiguous()
+        pk["mlp_b1"] = f32(self.mlp[2].linear.bias).contiguous() if self.mlp[2].linear.bias is not None else None
+        w1p, bsum, w1pl, w1inv, w2pl, w2inv, b2, wd, bd, dil = [], [], [], [], [], [], [], [], [], []
+        for blk in self.residual_layers:
+            wc = f32(blk.conv_layer.conv.weight)                     # [2C, C, 3]
+            wcond = f32(blk.conditioner_projection.conv.weight)[:, :, 0]   # [2C, E]
+            w1 = torch.cat([wc[:, :, 0], wc[:, :, 1], wc[:, :, 2], wcond], dim=1)[perm].contiguous()  # [2C, 3C+E]
+            w1p.append(w1)
+            bsum.append((f32(blk.conv_layer.conv.bias) + f32(blk.conditioner_projection.conv.bias))[perm])
+            p1, i1 = pack(w1)
+            w1pl.append(p1); w1inv.append(i1)
+            p2, i2 = pack(f32(blk.output_projection.conv.weight)[:, :, 0])
+            w2pl.append(p2); w2inv.append(i2)
+            b2.append(f32(blk.output_projection.conv.bias))
+            wd.append(f32(blk.diffusion_projection.linear.weight))
+            if blk.diffusion_projection.linear.bias is not None:
+                bd.append(f32(blk.diffusion_projection.linear.bias))
+            dil.append(blk.dilation)
+        pk["w1p_f32"] = torch.stack(w1p).contiguous()
+        pk["bias_sum"] = torch.stack(bsum).contiguous()
+        pk["w1"], pk["w1_inv"] = w1pl, w1inv
+        pk["w2"], pk["w2_inv"] = w2pl, w2inv
+        pk["b2"] = torch.stack(b2).contiguous()
+        pk["wd"] = torch.stack(wd).contiguous()
+        pk["bd"] = torch.stack(bd).contiguous() if bd else None
+        pk["dil"] = dil
+        pk["w_skip"], pk["w_skip_inv"] = pack(f32(self.skip_projection.conv.weight)[:, :, 0])
+        pk["b_skip"] = f32(self.skip_projection.conv.bias).contiguous()
+        pk["w_out"], pk["w_out_inv"] = pack(f32(self.output_projection.conv.weight)[:, :, 0])
+        pk["b_out"] = f32(self.output_projection.conv.bias).contiguous()
+        self._pack, self._pack_key = pk, key
+        return pk
+
+    def _workspace(self, device, B, T, Bs):
+        key = (str(device), B, T, Bs)
+        ws = self._ws.get(key)
+        if ws is None:
+            C, M, L = self.residual_channels, self.mel_channels, self.n_layers
+            i16 = dict(dtype=torch.int16, device=device)
+            f32 = dict(dtype=torch.float32, device=device)
+            ws = {
+                "xr": torch.empty((2, B, T, C), **i16), "z": torch.empty((2, B, T, C), **i16),
+                "skip_planes": torch.empty((2, B, T, C), **i16), "skip_f32": torch.empty((B, T, C), **f32),
+                "s": torch.empty((Bs, C), **f32), "mlp_ws": torch.empty((Bs * 5 * C,), **f32),
+                "gb": torch.empty((3, L, Bs, 2 * C), **f32), "gb_ws": torch.empty((L * Bs * C,), **f32),
+            }
+            self._ws = {key: ws}   # keep one shape resident
+        return ws
+
+    # ------------------------------------------------------------------------------------ native forward
+    @torch.no_grad()
+    def forward_cl(self, x_planes, steps, cond_planes, x_mask=None, out=None):
+        """Channels-last entry used by the fused sampler.
+
+        x_planes [2,B,T,M] int16 split planes, steps float32 [1] or [B] (device), cond_planes [2,B,T,E],
+        x_mask uint8/bool [B,T] or None (True = masked).  Returns eps fp32 [B,T,M]."""
+        dev = x_planes.device
+        N.require_cuda(x_planes, "x_planes")
+        _, B, T, M = x_planes.shape
+        C, E, L = self.residual_channels, self.d_encoder, self.n_layers
+        assert M == self.mel_channels and tuple(cond_planes.shape) == (2, B, T, E)
+        pk = self._packed(dev)
+        prec, backend = pk["prec"], pk["backend"]
+        steps = steps.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        Bs = steps.numel()
+        if Bs not in (1, B):
+            raise ValueError(f"diffusion_step must have 1 or B={B} entries, got {Bs}")
+        ws = self._workspace(dev, B, T, Bs)
+        st = N.stream_ptr(dev)
+        lib = N.lib()
+        if x_mask is not None:
+            x_mask = x_mask.to(device=dev, dtype=torch.uint8).contiguous()
+        if out is None:
+            out = torch.empty((B, T, M), dtype=torch.float32, device=dev)
+
+        N.check(lib.fd_wavenet_step_mlp(N.ptr(steps), N.ptr(pk["mlp_w0"]), N.ptr(pk["mlp_b0"]), N.ptr(pk["mlp_w1"]),
+                                        N.ptr(pk["mlp_b1"]), N.ptr(ws["s"]), N.ptr(ws["mlp_ws"]), Bs, C, st),
+                "fd_wavenet_step_mlp")
+        gb = ws["gb"]
+        N.check(lib.fd_wavenet_gate_bias(N.ptr(ws["s"]), N.ptr(pk["wd"]), N.ptr(pk["bd"]), N.ptr(pk["w1p_f32"]),
+                                         N.ptr(pk["bias_sum"]), N.ptr(gb[0]), N.ptr(gb[1]), N.ptr(gb[2]),
+                                         N.ptr(ws["gb_ws"]), L, Bs, C, 3 * C + E, st), "fd_wavenet_gate_bias")
+        # head: relu(input_projection(x)) with masked rows zeroed (wavenet.py:211-218)
+        N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], row_mask=x_mask, out_planes=ws["xr"],
+                  w_inv_scale=pk["w_in_inv"], act=N.ACT_RELU, prec=prec, backend=backend)
+        gb_stride = 2 * C if Bs > 1 else 0
+        skip_scale = 1.0 / math.sqrt(L)
+        for l in range(L):
+            flags = (1 if l == 0 else 0) | (2 if l == L - 1 else 0)
+            N.check(lib.fd_wavenet_block_fwd(
+                N.ptr(ws["xr"]), N.ptr(cond_planes), N.ptr(ws["z"]), N.ptr(pk["w1"][l]), N.ptr(pk["w2"][l]),
+                N.ptr(gb[0, l]), N.ptr(gb[1, l]), N.ptr(gb[2, l]), gb_stride, N.ptr(pk["b2"][l]),
+                N.ptr(ws["skip_f32"]), N.ptr(ws["skip_planes"]), skip_scale, B, T, C, E, pk["dil"][l],
+                pk["gate_tile"], pk["w1_inv"][l], pk["w2_inv"][l], flags, prec, backend, st), "fd_wavenet_block_fwd")
+        # tail: relu(skip_projection(sum/sqrt(L))) -> output_projection (+ mask) (wavenet.py:228-234)
+        N.conv_cl(ws["skip_planes"], pk["w_skip"], B, T, C, C, [0], bias=pk["b_skip"], out_planes=ws["z"],
+                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=prec, backend=backend)
+        N.conv_cl(ws["z"], pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], row_mask=x_mask, out_f32=out,
+                  w_inv_scale=pk["w_out_inv"], prec=prec, backend=backend)
+        return out
+
+    def forward(self, x, diffusion_step, conditioner, x_masks=None, cond_masks=None):
+        """Reference contract (wavenet.py:194-236): x [B,M,T] (or [B,1,M,T]), diffusion_step [B] or [1] (int64 or
+        float), conditioner [B,E,T], masks [B,T] bool -> [B,M,T] (4-D in -> 4-D out)."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # the backward (dgrad/wgrad tap-GEMMs) is the next row of the build plan; refuse rather than
+            # silently return a tensor that is detached from the graph
+            raise NotImplementedError(
+                "fish_diffusion_b200.WaveNet: autograd through the native kernels is not implemented yet; "
+                "call under torch.no_grad() (inference / sampling)")
+        use_4_dim = x.dim() == 4
+        if use_4_dim:
+            x = x[:, 0]
+        assert x.dim() == 3, f"mel must be 3 dim tensor, but got {x.dim()}"
+        N.require_cuda(x, "x")
+        prec = N.prec_code(self.precision)
+        B, M, T = x.shape
+        x_planes = N.split_ncw(x.to(torch.float32), prec)
+        cmask = None if cond_masks is None else cond_masks.to(torch.uint8).contiguous()
+        cond_planes = N.split_ncw(conditioner.to(torch.float32), prec, mask=cmask)
+        eps = self.forward_cl(x_planes, diffusion_step.to(torch.float32), cond_planes, x_mask=x_masks)
+        out = torch.empty((B, M, T), dtype=torch.float32, device=x.device)
+        N.check(N.lib().fd_transpose_nwc_to_ncw(N.ptr(eps), N.ptr(out), B, T, M, N.stream_ptr(x.device)),
+                "fd_transpose_nwc_to_ncw")
+        return out[:, None] if use_4_dim else out
+
+
+DENOISERS.register_module(name="WaveNetDenoiser", module=WaveNet, force=True)
+DENOISERS.register_module(name="B200WaveNetDenoiser", module=WaveNet, force=True)

@@ -315,9 +315,25 @@ def main():
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **out)
         print(f"{name}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
+    # state_dict key / shape inventories of the reference classes (drop-in boundary)
+    keys = {}
+    net = ref.wavenet.WaveNet(**WN_FULL)
+    keys["wavenet_full"] = {k: list(v.shape) for k, v in net.state_dict().items()}
+    net = ref.wavenet.WaveNet(**WN_NOBIAS)
+    keys["wavenet_nobias"] = {k: list(v.shape) for k, v in net.state_dict().items()}
+    diff = ref.diffusion.GaussianDiffusion(denoiser=dict(type="WaveNetDenoiser", **WN_SMALL), mel_channels=16,
+                                           spec_min=[-5.0], spec_max=[0.0])
+    keys["diffusion_small"] = {k: list(v.shape) for k, v in diff.state_dict().items()}
+    for name in ("config_v1", "config_v1_256"):
+        with open(f"{REF}/tools/nsf_hifigan/{name}.json") as f:
+            hh = ref.nsf.AttrDict(json.load(f))
+        g = ref.nsf.Generator(hh)
+        keys[f"generator_{name}_wn"] = {k: list(v.shape) for k, v in g.state_dict().items()}
+        g.remove_weight_norm()
+        keys[f"generator_{name}"] = {k: list(v.shape) for k, v in g.state_dict().items()}
     with open(os.path.join(HERE, "configs.json"), "w") as f:
-        json.dump(dict(WN_SMALL=WN_SMALL, WN_TC=WN_TC, WN_NOBIAS=WN_NOBIAS, WN_FULL=WN_FULL, VOC_SMALL=VOC_SMALL), f,
-                  indent=1)
+        json.dump(dict(WN_SMALL=WN_SMALL, WN_TC=WN_TC, WN_NOBIAS=WN_NOBIAS, WN_FULL=WN_FULL, VOC_SMALL=VOC_SMALL,
+                       state_dict_keys=keys), f, indent=1)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,46 @@
+"""CPU tests of the N>1 path: batch sharding over a world_size-2 gloo group (no data-path collective)."""
+import os
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+from fish_diffusion_b200.dist import gather_batch, item_seed, max_over_ranks, shard_range
+
+
+def test_shard_range_partitions():
+    for n in (1, 2, 5, 16, 32, 33):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert item_seed(3, 10) == item_seed(3, 10) != item_seed(3, 11)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    B = 5
+    full = torch.arange(B * 3, dtype=torch.float32).reshape(B, 3)
+    lo, hi = shard_range(B, rank, world)
+    # per-item work whose RNG stream depends on the GLOBAL item index only
+    local = torch.stack([full[i] * 2 + torch.Generator().manual_seed(item_seed(7, i) % (2 ** 31)).initial_seed() % 5
+                         for i in range(lo, hi)])
+    out = gather_batch(local, B)
+    want = torch.stack([full[i] * 2 + item_seed(7, i) % (2 ** 31) % 5 for i in range(B)])
+    ok = torch.equal(out, want)
+    t = max_over_ranks(1.0 + rank)
+    ret[rank] = (ok, t)
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_and_gather():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world))
+    assert all(ret[r][1] == 2.0 for r in range(world))          # max over ranks
