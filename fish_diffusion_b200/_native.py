@@ -41,6 +41,8 @@ _SIGS = {
     "fd_last_error": (c_char_p, []),
     "fd_launch_count": (c_longlong, []),
     "fd_tc_supported_linear": (c_int, [c_int, c_int, c_int]),
+    "fd_prof_enable": (None, [c_int]),
+    "fd_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_longlong), c_int]),
     "fd_split_ncw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fd_split_nwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "fd_transpose_nwc_to_ncw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -191,6 +193,25 @@ def conv_cl(in_planes, w_planes, B, T, Cin, N, shifts, *, bias=None, addend=None
     d.w_inv_scale, d.post_scale, d.planes_scale, d.act_slope = w_inv_scale, post_scale, planes_scale, act_slope
     d.out_accum, d.act, d.prec, d.backend = int(out_accum), act, prec, backend
     check(lib().fd_conv_cl_fwd(ctypes.byref(d), stream_ptr(in_planes.device)), "fd_conv_cl_fwd")
+
+
+PROF_KINDS = {0: "linear/tc", 1: "linear/simt", 2: "gate/tc", 3: "gate/simt", 4: "res_skip/tc", 5: "res_skip/simt",
+              6: "mag/tc", 7: "mag/simt"}
+
+
+def prof_enable(on: bool):
+    lib().fd_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """-> {kind name: (total ms, launches)} of every tap-GEMM launch since prof_enable(True)."""
+    n = len(PROF_KINDS)
+    ms = (ctypes.c_double * n)()
+    cnt = (c_longlong * n)()
+    rc = lib().fd_prof_collect(ms, cnt, n)
+    if rc < 0:
+        raise NativeError(f"fd_prof_collect failed: {last_error()}")
+    return {PROF_KINDS[k]: (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}, bool(rc)
 
 
 def tc_supported_linear(n_total: int, k_seg: int, num_seg: int) -> bool:

@@ -20,8 +20,35 @@ void set_src(FdTapGemm& p, int i, const uint16_t* ptr, int C) {
   p.src_ps[i] = (long long)p.B * p.T * C;
 }
 
+// ---- optional per-launch device timing (bench.py roofline): event pairs around every tap-GEMM launch
+constexpr int PROF_MAX = 1 << 16;
+bool g_prof_on = false;
+int g_prof_n = 0;
+cudaEvent_t* g_prof_ev = nullptr;   // 2 * PROF_MAX events, created lazily
+int g_prof_kind[PROF_MAX];
+
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  if (g_prof_ev == nullptr) {
+    g_prof_ev = new cudaEvent_t[2 * PROF_MAX];
+    for (int i = 0; i < 2 * PROF_MAX; ++i) g_prof_ev[i] = nullptr;
+  }
+  if (g_prof_ev[2 * g_prof_n] == nullptr) {
+    cudaEventCreate(&g_prof_ev[2 * g_prof_n]);
+    cudaEventCreate(&g_prof_ev[2 * g_prof_n + 1]);
+  }
+  g_prof_kind[g_prof_n] = kind;
+  cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st);
+  ++g_prof_n;
+}
+
 int run(const FdTapGemm& p, int backend, cudaStream_t st) {
   int rc;
+  prof_begin(p.epi * 2 + (backend == FD_BACKEND_TC ? 0 : 1), st);
   if (backend == FD_BACKEND_TC) {
     rc = fd_tapgemm_tc_launch(p, st);
   } else if (backend == FD_BACKEND_SIMT) {
@@ -30,6 +57,7 @@ int run(const FdTapGemm& p, int backend, cudaStream_t st) {
     fd_set_error("unknown backend %d", backend);
     return -2;
   }
+  prof_end(st);
   if (rc == 0) fd_count_launch(1);
   return rc;
 }
@@ -49,6 +77,25 @@ void fd_set_error(const char* fmt, ...) {
 const char* fd_last_error(void) { return g_err; }
 int fd_abi_version(void) { return FD_ABI_VERSION; }
 long long fd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void fd_prof_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+}
+
+int fd_prof_collect(double* ms_sum, long long* count, int nkinds) {
+  FD_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < nkinds; ++k) { ms_sum[k] = 0.0; count[k] = 0; }
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    FD_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+    const int k = g_prof_kind[i];
+    if (k < nkinds) { ms_sum[k] += ms; count[k] += 1; }
+  }
+  const int n = g_prof_n;
+  g_prof_n = 0;
+  return n >= PROF_MAX ? 1 : 0;
+}
 
 int fd_tc_supported_linear(int n_total, int k_seg, int num_seg) {
   FdTapGemm p;

@@ -35,6 +35,12 @@ int fd_abi_version(void);
 const char* fd_last_error(void);
 /* number of kernel launches issued by this library since process start (bench.py "gpu_launches") */
 long long fd_launch_count(void);
+/* per-launch device timing of the tap-GEMM kernels (CUDA events on the launching stream), used by bench.py for
+ * the roofline entry: kind = epilogue*2 + (backend==SIMT); epilogue 0 linear, 1 gate (WaveNet GEMM1),
+ * 2 res/skip (WaveNet GEMM2), 3 DFT magnitude.  fd_prof_collect synchronises the device, fills ms_sum[k]/count[k]
+ * for k < nkinds, resets the log and returns 1 if the log overflowed (65536 launches), 0 otherwise, <0 on error. */
+void fd_prof_enable(int on);
+int fd_prof_collect(double* ms_sum, long long* count, int nkinds);
 /* 1 if tensor-core instantiation exists for the given linear tap-GEMM shape */
 int fd_tc_supported_linear(int n_total, int k_seg, int num_seg);
 

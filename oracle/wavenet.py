@@ -16,10 +16,13 @@ def conv1d(x, w, b=None, dilation=1, padding=0, stride=1):
     xp = np.zeros((B, Ci, T + 2 * padding), dtype=x.dtype)
     xp[:, :, padding:padding + T] = x
     To = (T + 2 * padding - dilation * (K - 1) - 1) // stride + 1
-    out = np.zeros((B, Co, To), dtype=x.dtype)
-    for k in range(K):
-        seg = xp[:, :, k * dilation:k * dilation + (To - 1) * stride + 1:stride]
-        out += np.einsum("oi,bit->bot", w[:, :, k], seg, optimize=True)
+    out = np.empty((B, Co, To), dtype=x.dtype)
+    # one BLAS GEMM per item: W[Co, K*Ci] @ im2col[K*Ci, To]  (tap-major columns)
+    w2 = np.ascontiguousarray(np.transpose(w, (0, 2, 1)).reshape(Co, K * Ci))
+    for bi in range(B):
+        cols = np.concatenate([xp[bi, :, k * dilation:k * dilation + (To - 1) * stride + 1:stride] for k in range(K)],
+                              axis=0)
+        out[bi] = w2 @ cols
     if b is not None:
         out += b[None, :, None]
     return out
