@@ -226,7 +226,7 @@ def gold_sampler(ref, out):
 
 
 VOC_SMALL = dict(resblock="1", upsample_rates=[4, 4, 2, 2], upsample_kernel_sizes=[8, 8, 4, 4],
-                 upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11],
+                 upsample_initial_channel=128, resblock_kernel_sizes=[3, 7, 11],
                  resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], num_mels=32, hop_size=64,
                  sampling_rate=44100)
 

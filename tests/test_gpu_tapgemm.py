@@ -108,4 +108,4 @@ def test_tc_matches_simt_full_width_block():
         outs[name] = (planes_to_f64(xp, pc), skip.cpu().numpy().astype(np.float64), planes_to_f64(z, pc))
     for i, what in enumerate(("x", "skip", "z")):
         e = rel_l2(outs["tc"][i], outs["simt"][i])
-        assert e < 3e-6, (what, e)
+        assert e < 2e-5, (what, e)   # tensor-core fp32 accumulation truncates (not IEEE round-to-nearest)
