@@ -186,6 +186,25 @@ __device__ __forceinline__ void fd_load_planes(const uint16_t* planes, size_t pl
   for (int i = 0; i < V; ++i) y[i] = fd_combine(hi[i], lo[i], prec);
 }
 
+// register-level (un)packing of 8 consecutive channels; used by the split-phase (prefetch / finish) epilogues
+__device__ __forceinline__ void fd_unpack8(const uint4& a, const uint4& b, int prec, float (&y)[8]) {
+  const uint32_t ha[4] = {a.x, a.y, a.z, a.w}, lb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    y[2 * i] = fd_combine((uint16_t)(ha[i] & 0xffff), (uint16_t)(lb[i] & 0xffff), prec);
+    y[2 * i + 1] = fd_combine((uint16_t)(ha[i] >> 16), (uint16_t)(lb[i] >> 16), prec);
+  }
+}
+__device__ __forceinline__ void fd_pack8(const float (&y)[8], int prec, uint4& a, uint4& b) {
+  uint16_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fd_split(y[i], prec, hi[i], lo[i]);
+  a.x = hi[0] | ((uint32_t)hi[1] << 16); a.y = hi[2] | ((uint32_t)hi[3] << 16);
+  a.z = hi[4] | ((uint32_t)hi[5] << 16); a.w = hi[6] | ((uint32_t)hi[7] << 16);
+  b.x = lo[0] | ((uint32_t)lo[1] << 16); b.y = lo[2] | ((uint32_t)lo[3] << 16);
+  b.z = lo[4] | ((uint32_t)lo[5] << 16); b.w = lo[6] | ((uint32_t)lo[7] << 16);
+}
+
 template <int V>
 __device__ __forceinline__ void fd_load_f32(const float* p, float (&y)[V]) {
 #pragma unroll

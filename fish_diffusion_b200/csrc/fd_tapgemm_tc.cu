@@ -18,8 +18,9 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 256;                       // 8 epilogue warps
+constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -89,17 +90,41 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// issue a 16-column TMEM load without waiting; the registers are only valid after tmem_wait16 on the same array
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(&v[0]);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands so no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait16(float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(&v[0]);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// Warp-private 32x32 fp32 transpose through shared memory (16-byte chunks XOR-swizzled by row & 7, conflict-free
+// on both sides).  In: lane l owns row l (v[0..31]).  Out: a[p] = row (4p + l/8), columns 4*(l%8)..+3, i.e. eight
+// lanes cover one 128-byte row segment -> fully coalesced global accesses in the epilogue.
+__device__ __forceinline__ void warp_transpose_32x32(float* scratch, int lane, const float (&v)[32], float4 (&a)[8]) {
+  float4* s4 = reinterpret_cast<float4*>(scratch);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int k = 0; k < 8; ++k)
+    s4[lane * 8 + (k ^ (lane & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+  const int j = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) {
+    const int r = pp * 4 + rsub;
+    a[pp] = s4[r * 8 + (j ^ (r & 7))];
+  }
+  __syncwarp();
 }
 
 // K-major operand descriptor (see cute::UMMA::SmemDescriptor): start addr>>4 [0,14), LBO>>4 [16,30),
@@ -114,7 +139,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   return d;
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, int EPI>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int W_BYTES_RAW = BLOCK_N * BLOCK_K * 2;
@@ -130,16 +155,19 @@ struct Cfg {
   static constexpr int SWIZZLE_BYTES = BLOCK_K * 2;                       // 128 / 64 / 32
   static constexpr uint32_t LAYOUT_TYPE = BLOCK_K == 64 ? 2u : BLOCK_K == 32 ? 4u : 6u;
   static constexpr uint32_t SBO = 8 * SWIZZLE_BYTES;
-  static constexpr int BIAS_FLOATS = 3 * BLOCK_N;
+  static constexpr int BIAS_FLOATS = (EPI == FD_EPI_GATE ? 3 : 1) * BLOCK_N;
+  // coalescing epilogue (LINEAR / RES_SKIP with >= 32 columns per warp): a 32x32 fp32 transpose scratch per warp
+  static constexpr bool COALESCED = (EPI == FD_EPI_LINEAR || EPI == FD_EPI_RES_SKIP) && BLOCK_N >= 64;
+  static constexpr int SCRATCH_BYTES = COALESCED ? (EPI_THREADS / 32) * 4096 : 0;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + BIAS_FLOATS * 4 +
-                                    (2 * NUM_STAGES + 2 * ACC_STAGES) * 8 + 16;
+                                    (2 * NUM_STAGES + 2 * ACC_STAGES) * 8 + 16 + SCRATCH_BYTES;
 };
 
 template <int BLOCK_N, int BLOCK_K, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                      const __grid_constant__ CUtensorMap tm_w, const FdTapGemm p) {
-  using C = Cfg<BLOCK_N, BLOCK_K>;
+  using C = Cfg<BLOCK_N, BLOCK_K, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -149,6 +177,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
   uint64_t* tfull_bar = empty_bar + C::NUM_STAGES;
   uint64_t* tempty_bar = tfull_bar + C::ACC_STAGES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + C::ACC_STAGES);
+  float* scratch_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // 16-byte aligned (all preceding sizes are)
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -165,7 +194,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_THREADS / 32); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -243,10 +272,13 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // =========================================================== epilogue
-    const int q = warp % 4;                 // TMEM lane quadrant this warp may access
+    // =========================================================== epilogue (8 warps)
+    // warp w may access TMEM lanes [32*(w%4), +32); the two warps of a lane quadrant split the columns.
+    const int q = warp % 4;
+    const int half = (warp - EPI_WARP0) / 4;
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - EPI_WARP0 * 32;   // 0..127
+    const int etid = threadIdx.x - EPI_WARP0 * 32;   // 0..255
+    constexpr int HALVES = BLOCK_N >= 64 ? 2 : 1;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
@@ -256,39 +288,44 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
       const bool valid = t < p.T;
 
       // stage the per-column bias vectors of this tile in shared memory
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (EPI == FD_EPI_MAG) {
         // no bias
       } else if (EPI == FD_EPI_GATE) {
         const size_t bo = (size_t)b * p.gbias_bstride + n0;
-        for (int i = etid; i < BLOCK_N; i += 128) {
+        for (int i = etid; i < BLOCK_N; i += EPI_THREADS) {
           bias_s[i] = p.gbias_full[bo + i];
           bias_s[BLOCK_N + i] = p.gbias_lo[bo + i];
           bias_s[2 * BLOCK_N + i] = p.gbias_hi[bo + i];
         }
       } else {
-        for (int i = etid; i < BLOCK_N; i += 128)
+        for (int i = etid; i < BLOCK_N; i += EPI_THREADS)
           bias_s[i] = p.bias ? p.bias[(size_t)b * p.bias_bstride + n0 + i] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
 
       if (EPI == FD_EPI_GATE || EPI == FD_EPI_MAG) {
-        constexpr int HALF = BLOCK_N / 2;
-        for (int c = 0; c < HALF; c += 16) {
+        constexpr int HALF = BLOCK_N / 2;       // gate columns | filter columns
+        constexpr int PER = HALF / 2;           // gate columns handled by this warp
+        const int cb = half * PER;
+        for (int c = 0; c < PER; c += 16) {
+          const int c0 = cb + c;
           float g[16], f[16];
-          tmem_ld16(taddr + c, g);
-          tmem_ld16(taddr + HALF + c, f);
+          tmem_ld16_nowait(taddr + c0, g);
+          tmem_ld16_nowait(taddr + HALF + c0, f);
+          tmem_wait16(g);
+          tmem_wait16(f);
           if (valid) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float g8[8], f8[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) { g8[i] = g[h * 8 + i]; f8[i] = f[h * 8 + i]; }
-              const int cc = c + h * 8;
+              const int cc = c0 + h * 8;
               if (EPI == FD_EPI_MAG)
                 fd_epi_mag<8>(p, b, t, n_tile * HALF + cc, g8, f8);
               else
@@ -298,19 +335,164 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
             }
           }
         }
+      } else if (C::COALESCED) {
+        // ---- LINEAR / RES_SKIP, coalescing epilogue: 32-column chunks, accumulators transposed through a warp-private
+        //      smem scratch so that 8 lanes cover one 128-byte row segment; all global loads of a half-chunk are issued
+        //      before the TMEM wait (latency overlap); per-item math is the shared V=4 epilogue of fd_common.cuh order.
+        constexpr int PER = BLOCK_N / HALVES;
+        float* my_scratch = scratch_s + (warp - EPI_WARP0) * 1024;
+        const int j4 = (lane & 7) * 4, rsub = lane >> 3;
+        const int rbase = t0 + q * 32 + rsub;            // time index of pass 0
+        for (int c = 0; c < PER; c += 32) {
+          const int col = half * PER + c + j4;           // first of this lane's 4 columns inside the tile
+          const int n = n0 + col;                        // global packed column
+          float v[32];
+          tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
+          tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+          const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + col);
+          if (EPI == FD_EPI_RES_SKIP) {
+            const bool is_res = n0 < p.C;
+            const size_t plane = (size_t)p.B * p.T * p.C;
+            uint4 op[8];     // residual tile: .xy = hi-plane words, .zw = lo-plane words; skip tile: 4 floats
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const int tt = rbase + pp * 4;
+              if (tt < p.T) {
+                const size_t ro = ((size_t)b * p.T + tt) * p.C;
+                if (is_res) {
+                  if (!p.last_layer) {
+                    const uint2 h2 = *reinterpret_cast<const uint2*>(p.x_planes + ro + n);
+                    const uint2 l2 = *reinterpret_cast<const uint2*>(p.x_planes + plane + ro + n);
+                    op[pp] = make_uint4(h2.x, h2.y, l2.x, l2.y);
+                  }
+                } else if (!p.first_layer) {
+                  op[pp] = *reinterpret_cast<const uint4*>(p.skip_f32 + ro + (n - p.C));
+                }
+              }
+            }
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[16]));
+            float4 a[8];
+            warp_transpose_32x32(my_scratch, lane, v, a);
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const int tt = rbase + pp * 4;
+              if (tt >= p.T) continue;
+              const size_t ro = ((size_t)b * p.T + tt) * p.C;
+              float y[4] = {a[pp].x * p.acc_scale + bias4.x, a[pp].y * p.acc_scale + bias4.y,
+                            a[pp].z * p.acc_scale + bias4.z, a[pp].w * p.acc_scale + bias4.w};
+              if (is_res) {
+                if (p.last_layer) continue;
+                const uint4 o = op[pp];
+                float x4[4];
+                x4[0] = fd_combine((uint16_t)(o.x & 0xffff), (uint16_t)(o.z & 0xffff), p.prec);
+                x4[1] = fd_combine((uint16_t)(o.x >> 16), (uint16_t)(o.z >> 16), p.prec);
+                x4[2] = fd_combine((uint16_t)(o.y & 0xffff), (uint16_t)(o.w & 0xffff), p.prec);
+                x4[3] = fd_combine((uint16_t)(o.y >> 16), (uint16_t)(o.w >> 16), p.prec);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x4[i] = (x4[i] + y[i]) * 0.70710678118654752440f;
+                fd_store_planes<4>(p.x_planes, plane, ro + n, x4, p.prec);
+              } else {
+                if (!p.first_layer) {
+                  const uint4 o = op[pp];
+                  y[0] += __uint_as_float(o.x); y[1] += __uint_as_float(o.y);
+                  y[2] += __uint_as_float(o.z); y[3] += __uint_as_float(o.w);
+                }
+                if (p.last_layer) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) y[i] *= p.skip_scale;
+                  fd_store_planes<4>(p.skip_planes, plane, ro + (n - p.C), y, p.prec);
+                } else {
+                  *reinterpret_cast<float4*>(p.skip_f32 + ro + (n - p.C)) = make_float4(y[0], y[1], y[2], y[3]);
+                }
+              }
+            }
+          } else {
+            // LINEAR
+            const size_t plane = (size_t)p.B * p.T * p.n_total;
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[16]));
+            float4 a[8];
+            warp_transpose_32x32(my_scratch, lane, v, a);
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {          // two groups of 4 passes: bounded register use, 4-deep load batches
+              float4 ad[4], rs[4], pv[4];
+              uint2 rh[4], rl[4];
+              bool mk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int tt = rbase + (hp * 4 + k) * 4;
+                mk[k] = false;
+                if (tt < p.T) {
+                  const size_t gro = (size_t)b * p.T + tt;
+                  const size_t off = gro * p.n_total + n;
+                  if (p.addend != nullptr) ad[k] = *reinterpret_cast<const float4*>(p.addend + off);
+                  if (p.res_f32 != nullptr) rs[k] = *reinterpret_cast<const float4*>(p.res_f32 + off);
+                  if (p.res_planes != nullptr) {
+                    rh[k] = *reinterpret_cast<const uint2*>(p.res_planes + off);
+                    rl[k] = *reinterpret_cast<const uint2*>(p.res_planes + plane + off);
+                  }
+                  if (p.out_f32 != nullptr && p.out_accum) pv[k] = *reinterpret_cast<const float4*>(p.out_f32 + off);
+                  if (p.row_mask != nullptr) mk[k] = p.row_mask[gro] != 0;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int pp = hp * 4 + k;
+                const int tt = rbase + pp * 4;
+                if (tt >= p.T) continue;
+                const size_t off = ((size_t)b * p.T + tt) * p.n_total + n;
+                float y[4] = {a[pp].x * p.acc_scale + bias4.x, a[pp].y * p.acc_scale + bias4.y,
+                              a[pp].z * p.acc_scale + bias4.z, a[pp].w * p.acc_scale + bias4.w};
+                if (p.addend != nullptr) { y[0] += ad[k].x; y[1] += ad[k].y; y[2] += ad[k].z; y[3] += ad[k].w; }
+                if (p.res_f32 != nullptr) { y[0] += rs[k].x; y[1] += rs[k].y; y[2] += rs[k].z; y[3] += rs[k].w; }
+                if (p.res_planes != nullptr) {
+                  y[0] += fd_combine((uint16_t)(rh[k].x & 0xffff), (uint16_t)(rl[k].x & 0xffff), p.prec);
+                  y[1] += fd_combine((uint16_t)(rh[k].x >> 16), (uint16_t)(rl[k].x >> 16), p.prec);
+                  y[2] += fd_combine((uint16_t)(rh[k].y & 0xffff), (uint16_t)(rl[k].y & 0xffff), p.prec);
+                  y[3] += fd_combine((uint16_t)(rh[k].y >> 16), (uint16_t)(rl[k].y >> 16), p.prec);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] *= p.post_scale;
+                if (p.out_f32 != nullptr) {
+                  if (p.out_accum) { y[0] += pv[k].x; y[1] += pv[k].y; y[2] += pv[k].z; y[3] += pv[k].w; }
+                  if (mk[k]) { y[0] = y[1] = y[2] = y[3] = 0.f; }
+                  *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+                }
+                if (p.out_planes != nullptr) {
+                  float o4[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float w = y[i] * p.planes_scale;
+                    if (p.act == FD_ACT_RELU) w = fmaxf(w, 0.f);
+                    else if (p.act == FD_ACT_LRELU) w = w > 0.f ? w : w * p.act_slope;
+                    o4[i] = mk[k] ? 0.f : w;
+                  }
+                  fd_store_planes<4>(p.out_planes, plane, off, o4, p.prec);
+                }
+              }
+            }
+          }
+        }
       } else {
-        for (int c = 0; c < BLOCK_N; c += 16) {
-          float v[16];
-          tmem_ld16(taddr + c, v);
-          if (valid) {
+        // ---- LINEAR / RES_SKIP with narrow tiles (BLOCK_N <= 32): row-owner epilogue, 16-column chunks
+        constexpr int PER = BLOCK_N / HALVES;
+        if (half < HALVES) {
+          for (int c = 0; c < PER; c += 16) {
+            const int col = half * PER + c;
+            float v[16];
+            tmem_ld16_nowait(taddr + col, v);
+            tmem_wait16(v);
+            if (valid) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float v8[8];
+              for (int h = 0; h < 2; ++h) {
+                float v8[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v8[i] = v[h * 8 + i];
-              const int cc = c + h * 8;
-              if (EPI == FD_EPI_LINEAR) fd_epi_linear<8>(p, b, t, n0 + cc, v8, bias_s, n0);
-              else fd_epi_res_skip<8>(p, b, t, n0 + cc, v8, bias_s + cc);
+                for (int i = 0; i < 8; ++i) v8[i] = v[h * 8 + i];
+                const int cc = col + h * 8;
+                if (EPI == FD_EPI_LINEAR) fd_epi_linear<8>(p, b, t, n0 + cc, v8, bias_s, n0);
+                else fd_epi_res_skip<8>(p, b, t, n0 + cc, v8, bias_s + cc);
+              }
             }
           }
         }
@@ -391,7 +573,7 @@ int g_num_sms = 0;
 
 template <int BLOCK_N, int BLOCK_K, int EPI>
 int launch_cfg(const FdTapGemm& p, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, BLOCK_K>;
+  using C = Cfg<BLOCK_N, BLOCK_K, EPI>;
   CUtensorMap tm0, tm1, tmw;
   int rc = make_src_map(&tm0, p.src[0], p.B, p.T, p.src_C[0], p.src_rs[0], p.src_bs[0], p.src_ps[0], BLOCK_K);
   if (rc) return rc;
