@@ -36,7 +36,31 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class GemmDesc(ctypes.Structure):
+    """struct fd_gemm_desc (include/fishdiff_b200.h)."""
+    _fields_ = [
+        ("src", c_void_p * 2), ("src_C", c_int * 2), ("src_rs", c_longlong * 2), ("src_bs", c_longlong * 2),
+        ("src_ps", c_longlong * 2), ("w", c_void_p), ("n_total", c_int), ("k_total", c_int), ("w_kshift", c_int),
+        ("w_bstride_k", c_longlong), ("B", c_int), ("T", c_int), ("num_seg", c_int), ("seg_src", c_int * 16),
+        ("seg_shift", c_int * 16), ("seg_coff", c_int * 16), ("seg_klen", c_int * 16),
+        ("bias", c_void_p), ("addend", c_void_p), ("res_f32", c_void_p), ("res_planes", c_void_p),
+        ("row_mask", c_void_p), ("out_f32", c_void_p), ("out_planes", c_void_p),
+        ("w_inv_scale", c_float), ("res_scale", c_float), ("post_scale", c_float), ("planes_scale", c_float),
+        ("act_slope", c_float), ("out_accum", c_int), ("act", c_int), ("prec", c_int), ("backend", c_int),
+    ]
+
+
 _SIGS = {
+    "fd_gemm_cl_fwd": (c_int, [POINTER(GemmDesc), c_void_p]),
+    "fd_wavenet_block_fwd_train": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_void_p, c_float] +
+                                   [c_int] * 6 + [c_float, c_float, c_int, c_int, c_int, c_void_p]),
+    "fd_wavenet_gate_bias_from_d": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "fd_fold_transpose": (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 5 + [c_float, c_int, c_int, c_int,
+                                                                                   c_void_p]),
+    "fd_gate_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_int, c_int, c_int, c_void_p]),
+    "fd_relu_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_float, c_int, c_void_p]),
+    "fd_colsum": (c_int, [c_void_p] * 3 + [c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "fd_reduce_batch": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_float, c_void_p]),
     "fd_abi_version": (c_int, []),
     "fd_last_error": (c_char_p, []),
     "fd_launch_count": (c_longlong, []),
@@ -216,3 +240,27 @@ def prof_collect():
 
 def tc_supported_linear(n_total: int, k_seg: int, num_seg: int) -> bool:
     return bool(lib().fd_tc_supported_linear(n_total, k_seg, num_seg))
+
+
+def gemm_cl(src0, C0, w_planes, n_total, k_total, B, T, segs, *, src1=None, C1=0, strides0=None, strides1=None,
+            w_kshift=0, w_bstride_k=0, bias=None, addend=None, res_f32=None, res_planes=None, res_scale=1.0,
+            row_mask=None, out_f32=None, out_planes=None, w_inv_scale=1.0, post_scale=1.0, planes_scale=1.0,
+            act=ACT_NONE, act_slope=0.0, out_accum=False, prec=PREC_F16, backend=BACKEND_TC):
+    """General linear tap-GEMM (fd_gemm_cl_fwd).  segs = [(src_index, shift, c_off, k_len), ...];
+    stridesX = (row_stride, batch_stride, plane_stride) in elements or None for the canonical [2][B][T][C]."""
+    d = GemmDesc()
+    d.src[0], d.src_C[0] = ptr(src0), C0
+    d.src[1], d.src_C[1] = ptr(src1), C1
+    for i, st in enumerate((strides0, strides1)):
+        if st is not None:
+            d.src_rs[i], d.src_bs[i], d.src_ps[i] = st
+    d.w, d.n_total, d.k_total, d.w_kshift, d.w_bstride_k = ptr(w_planes), n_total, k_total, int(w_kshift), int(w_bstride_k)
+    d.B, d.T, d.num_seg = B, T, len(segs)
+    for j, (si, sh, co, kl) in enumerate(segs):
+        d.seg_src[j], d.seg_shift[j], d.seg_coff[j], d.seg_klen[j] = si, sh, co, kl
+    d.bias, d.addend, d.res_f32, d.res_planes = ptr(bias), ptr(addend), ptr(res_f32), ptr(res_planes)
+    d.row_mask, d.out_f32, d.out_planes = ptr(row_mask), ptr(out_f32), ptr(out_planes)
+    d.w_inv_scale, d.res_scale, d.post_scale = w_inv_scale, res_scale, post_scale
+    d.planes_scale, d.act_slope = planes_scale, act_slope
+    d.out_accum, d.act, d.prec, d.backend = int(out_accum), act, prec, backend
+    check(lib().fd_gemm_cl_fwd(ctypes.byref(d), stream_ptr(src0.device)), "fd_gemm_cl_fwd")

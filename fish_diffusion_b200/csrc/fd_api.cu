@@ -10,7 +10,7 @@ namespace {
 thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
 
-void init_desc(FdTapGemm& p) { memset(&p, 0, sizeof(p)); p.acc_scale = 1.f; p.post_scale = 1.f; p.planes_scale = 1.f; }
+void init_desc(FdTapGemm& p) { memset(&p, 0, sizeof(p)); p.acc_scale = 1.f; p.post_scale = 1.f; p.planes_scale = 1.f; p.res_scale = 1.f; }
 
 void set_src(FdTapGemm& p, int i, const uint16_t* ptr, int C) {
   p.src[i] = ptr;
@@ -108,11 +108,41 @@ int fd_tc_supported_linear(int n_total, int k_seg, int num_seg) {
   return fd_tapgemm_tc_supported(p);
 }
 
+static int wavenet_block(const uint16_t* x_planes, uint16_t* x_out_planes, const uint16_t* cond_planes,
+                         uint16_t* z_planes, uint16_t* y_planes, const uint16_t* w1, const uint16_t* w2,
+                         const float* gb_full, const float* gb_lo, const float* gb_hi, int gb_bstride, const float* b2,
+                         float* skip_f32, uint16_t* skip_planes, float skip_scale, int B, int T, int C, int E,
+                         int dilation, int gate_tile, float w1_inv_scale, float w2_inv_scale, int flags, int prec,
+                         int backend, void* stream);
+
 int fd_wavenet_block_fwd(uint16_t* x_planes, const uint16_t* cond_planes, uint16_t* z_planes, const uint16_t* w1,
                          const uint16_t* w2, const float* gb_full, const float* gb_lo, const float* gb_hi,
                          int gb_bstride, const float* b2, float* skip_f32, uint16_t* skip_planes, float skip_scale,
                          int B, int T, int C, int E, int dilation, int gate_tile, float w1_inv_scale,
                          float w2_inv_scale, int flags, int prec, int backend, void* stream) {
+  return wavenet_block(x_planes, nullptr, cond_planes, z_planes, nullptr, w1, w2, gb_full, gb_lo, gb_hi, gb_bstride, b2,
+                       skip_f32, skip_planes, skip_scale, B, T, C, E, dilation, gate_tile, w1_inv_scale, w2_inv_scale,
+                       flags, prec, backend, stream);
+}
+
+int fd_wavenet_block_fwd_train(const uint16_t* x_planes, uint16_t* x_out_planes, const uint16_t* cond_planes,
+                               uint16_t* z_planes, uint16_t* y_planes, const uint16_t* w1, const uint16_t* w2,
+                               const float* gb_full, const float* gb_lo, const float* gb_hi, int gb_bstride,
+                               const float* b2, float* skip_f32, uint16_t* skip_planes, float skip_scale, int B, int T,
+                               int C, int E, int dilation, int gate_tile, float w1_inv_scale, float w2_inv_scale,
+                               int flags, int prec, int backend, void* stream) {
+  FD_REQUIRE(x_out_planes != nullptr && y_planes != nullptr, "fd_wavenet_block_fwd_train: x_out / y planes required");
+  return wavenet_block(x_planes, x_out_planes, cond_planes, z_planes, y_planes, w1, w2, gb_full, gb_lo, gb_hi,
+                       gb_bstride, b2, skip_f32, skip_planes, skip_scale, B, T, C, E, dilation, gate_tile, w1_inv_scale,
+                       w2_inv_scale, flags, prec, backend, stream);
+}
+
+static int wavenet_block(const uint16_t* x_planes, uint16_t* x_out_planes, const uint16_t* cond_planes,
+                         uint16_t* z_planes, uint16_t* y_planes, const uint16_t* w1, const uint16_t* w2,
+                         const float* gb_full, const float* gb_lo, const float* gb_hi, int gb_bstride, const float* b2,
+                         float* skip_f32, uint16_t* skip_planes, float skip_scale, int B, int T, int C, int E,
+                         int dilation, int gate_tile, float w1_inv_scale, float w2_inv_scale, int flags, int prec,
+                         int backend, void* stream) {
   FD_REQUIRE(B > 0 && T > 0 && C > 0 && E > 0 && dilation > 0, "fd_wavenet_block_fwd: bad shape");
   FD_REQUIRE(C % 8 == 0 && E % 8 == 0, "fd_wavenet_block_fwd: C=%d, E=%d must be multiples of 8", C, E);
   cudaStream_t st = (cudaStream_t)stream;
@@ -132,6 +162,7 @@ int fd_wavenet_block_fwd(uint16_t* x_planes, const uint16_t* cond_planes, uint16
   p.gbias_full = gb_full; p.gbias_lo = gb_lo; p.gbias_hi = gb_hi; p.gbias_bstride = gb_bstride;
   p.dil = dilation; p.gate_tile = gate_tile; p.C = C;
   p.out_planes = z_planes;
+  p.y_planes = y_planes;
   int rc = run(p, backend, st);
   if (rc) return rc;
   // ---- GEMM2: output projection + residual / skip
@@ -144,7 +175,7 @@ int fd_wavenet_block_fwd(uint16_t* x_planes, const uint16_t* cond_planes, uint16
   q.w = w2; q.acc_scale = w2_inv_scale;
   q.epi = FD_EPI_RES_SKIP;
   q.bias = b2; q.bias_bstride = 0;
-  q.x_planes = x_planes; q.skip_f32 = skip_f32; q.skip_planes = skip_planes; q.skip_scale = skip_scale;
+  q.x_planes = const_cast<uint16_t*>(x_planes); q.x_out_planes = x_out_planes; q.skip_f32 = skip_f32; q.skip_planes = skip_planes; q.skip_scale = skip_scale;
   q.first_layer = flags & 1; q.last_layer = (flags >> 1) & 1; q.C = C;
   return run(q, backend, st);
 }
@@ -187,6 +218,36 @@ int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag
   p.epi = FD_EPI_MAG; p.gate_tile = 256; p.C = NB; p.mag_scale = mag_scale;
   p.out_planes = mag_planes;
   return run(p, backend, (cudaStream_t)stream);
+}
+
+int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream) {
+  FD_REQUIRE(d != nullptr, "fd_gemm_cl_fwd: null descriptor");
+  FD_REQUIRE(d->num_seg >= 1 && d->num_seg <= FD_MAX_SEG, "fd_gemm_cl_fwd: num_seg=%d out of range", d->num_seg);
+  FD_REQUIRE(d->B > 0 && d->T > 0 && d->n_total > 0 && d->k_total > 0, "fd_gemm_cl_fwd: bad shape");
+  FdTapGemm p;
+  init_desc(p);
+  p.B = d->B; p.T = d->T; p.prec = d->prec;
+  p.n_total = d->n_total; p.k_total = d->k_total; p.num_seg = d->num_seg;
+  for (int j = 0; j < d->num_seg; ++j) {
+    FD_REQUIRE(d->seg_src[j] == 0 || d->seg_src[j] == 1, "fd_gemm_cl_fwd: segment %d has bad source", j);
+    p.seg[j] = FdSeg{d->seg_src[j], d->seg_shift[j], d->seg_coff[j], d->seg_klen[j]};
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (d->src[i] == nullptr) continue;
+    set_src(p, i, d->src[i], d->src_C[i]);
+    if (d->src_rs[i] != 0) p.src_rs[i] = d->src_rs[i];
+    if (d->src_bs[i] != 0) p.src_bs[i] = d->src_bs[i];
+    if (d->src_ps[i] != 0) p.src_ps[i] = d->src_ps[i];
+  }
+  FD_REQUIRE(p.src[0] != nullptr, "fd_gemm_cl_fwd: src[0] is null");
+  p.w = d->w; p.acc_scale = d->w_inv_scale; p.w_kshift = d->w_kshift; p.w_bstride_k = d->w_bstride_k;
+  p.epi = FD_EPI_LINEAR;
+  p.bias = d->bias; p.bias_bstride = 0;
+  p.addend = d->addend; p.res_f32 = d->res_f32; p.res_planes = d->res_planes; p.res_scale = d->res_scale;
+  p.post_scale = d->post_scale; p.out_f32 = d->out_f32; p.out_accum = d->out_accum;
+  p.out_planes = d->out_planes; p.planes_scale = d->planes_scale; p.act = d->act; p.act_slope = d->act_slope;
+  p.row_mask = d->row_mask;
+  return run(p, d->backend, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -325,6 +325,15 @@ int fd_wavenet_gate_bias(const float* s, const float* wd, const float* bd, const
   return 0;
 }
 
+int fd_wavenet_gate_bias_from_d(const float* d, const float* w1p, const float* bias_sum, float* gb_full, float* gb_lo,
+                                float* gb_hi, int L, int Bs, int C, int KT, void* stream) {
+  const long long warps = (long long)L * Bs * 2 * C;
+  k_gate_bias<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, w1p, bias_sum, gb_full, gb_lo,
+                                                                                       gb_hi, L, Bs, C, KT);
+  FD_LAUNCHED();
+  return 0;
+}
+
 int fd_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, uint16_t* x_planes,
                  long long n, float c_recip, float c_recipm1, float c1, float c2, float sigma, float clip_min,
                  float clip_max, unsigned long long seed, unsigned long long offset, int prec, void* stream) {

@@ -51,6 +51,10 @@ struct FdTapGemm {
   long long src_rs[2], src_bs[2], src_ps[2];
   const uint16_t* w;        // split planes [2][n_total][k_total]
   float acc_scale;          // accumulators are multiplied by this (undoes power-of-two weight prescale)
+  // W-operand K offsets (weight-gradient GEMMs, where "W" is a transposed activation tensor [rows][B*Tp]):
+  // the K coordinate of the W operand is  koff(seg) + k0 + w_kshift + b * w_bstride_k
+  int w_kshift;
+  long long w_bstride_k;
   int epi;
 
   // ---- FD_EPI_LINEAR:  y = acc*acc_scale + bias[n] + addend[b,t,n] + res[b,t,n];  y *= post_scale
@@ -62,6 +66,7 @@ struct FdTapGemm {
   const float* addend;      // fp32 [B,T,n_total] or null
   const float* res_f32;     // fp32 [B,T,n_total] or null
   const uint16_t* res_planes;  // split planes [2][B][T][n_total] or null
+  float res_scale;          // multiplies the res_planes term (gradient chains: dx_next / sqrt(2))
   float post_scale;
   float* out_f32;           // fp32 [B,T,n_total] or null
   int out_accum;
@@ -90,6 +95,8 @@ struct FdTapGemm {
   //      x' = (x + y_res) / sqrt(2)  -> x planes updated in place
   //      skip: first_layer ? skip_f32 = y : skip_f32 += y ; last_layer: skip planes = split((skip_f32+y)*skip_scale)
   uint16_t* x_planes;       // [2][B][T][C] in/out
+  uint16_t* x_out_planes;   // training: write the updated residual stream here instead of in place (or null)
+  uint16_t* y_planes;       // training (GATE epilogue): pre-activations [2][B][T][2C] in packed column order (or null)
   float* skip_f32;          // [B,T,C]
   uint16_t* skip_planes;    // [2][B][T][C] (last layer only)
   float skip_scale;
@@ -252,7 +259,7 @@ __device__ __forceinline__ void fd_epi_linear(const FdTapGemm& p, int b, int t, 
   if (p.res_planes != nullptr) {
     float a[V]; fd_load_planes<V>(p.res_planes, plane_elems, off, a, p.prec);
 #pragma unroll
-    for (int i = 0; i < V; ++i) y[i] += a[i];
+    for (int i = 0; i < V; ++i) y[i] += a[i] * p.res_scale;
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) y[i] *= p.post_scale;
@@ -288,7 +295,7 @@ __device__ __forceinline__ void fd_epi_gate(const FdTapGemm& p, int b, int t, in
                                             const float* full_g, const float* full_f,
                                             const float* lo_g, const float* lo_f,
                                             const float* hi_g, const float* hi_f) {
-  float z[V];
+  float z[V], yg8[V], yf8[V];
   const bool e_lo = t < p.dil, e_hi = t + p.dil >= p.T;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -296,7 +303,16 @@ __device__ __forceinline__ void fd_epi_gate(const FdTapGemm& p, int b, int t, in
     float yf = f[i] * p.acc_scale + full_f[i];
     if (e_lo) { yg -= lo_g[i]; yf -= lo_f[i]; }
     if (e_hi) { yg -= hi_g[i]; yf -= hi_f[i]; }
+    yg8[i] = yg; yf8[i] = yf;
     z[i] = fd_sigmoid(yg) * fd_tanh(yf);
+  }
+  if (p.y_planes != nullptr) {   // training: keep the pre-activations (packed column order: gates | filters per tile)
+    const int half = p.gate_tile / 2;
+    const int ng = (zc0 / half) * p.gate_tile + (zc0 % half);
+    const size_t yplane = (size_t)p.B * p.T * p.n_total;
+    const size_t yoff = ((size_t)b * p.T + t) * p.n_total;
+    fd_store_planes<V>(p.y_planes, yplane, yoff + ng, yg8, p.prec);
+    fd_store_planes<V>(p.y_planes, yplane, yoff + ng + half, yf8, p.prec);
   }
   const size_t plane_elems = (size_t)p.B * p.T * p.C;
   const size_t off = ((size_t)b * p.T + t) * p.C + zc0;
@@ -333,7 +349,7 @@ __device__ __forceinline__ void fd_epi_res_skip(const FdTapGemm& p, int b, int t
     fd_load_planes<V>(p.x_planes, plane_elems, off, x, p.prec);
 #pragma unroll
     for (int i = 0; i < V; ++i) x[i] = (x[i] + y[i]) * 0.70710678118654752440f;
-    fd_store_planes<V>(p.x_planes, plane_elems, off, x, p.prec);
+    fd_store_planes<V>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane_elems, off, x, p.prec);
   } else {
     const size_t off = row * p.C + (n0 - p.C);
     if (!p.first_layer) {

@@ -226,8 +226,9 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
             mbar_expect_tx(&full_bar[stage], C::TX_BYTES);
             tma_load_4d(st, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 0);
             tma_load_4d(st + C::A_BYTES, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 1);
-            tma_load_3d(st + 2 * C::A_BYTES, &tm_w, &full_bar[stage], koff + k0, n0, 0);
-            tma_load_3d(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w, &full_bar[stage], koff + k0, n0, 1);
+            const int kw = koff + k0 + p.w_kshift + (int)(b * p.w_bstride_k);
+            tma_load_3d(st + 2 * C::A_BYTES, &tm_w, &full_bar[stage], kw, n0, 0);
+            tma_load_3d(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w, &full_bar[stage], kw, n0, 1);
             if (++stage == C::NUM_STAGES) { stage = 0; phase ^= 1; }
           }
           koff += sg.k_len;
@@ -391,7 +392,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 x4[3] = fd_combine((uint16_t)(o.y >> 16), (uint16_t)(o.w >> 16), p.prec);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) x4[i] = (x4[i] + y[i]) * 0.70710678118654752440f;
-                fd_store_planes<4>(p.x_planes, plane, ro + n, x4, p.prec);
+                fd_store_planes<4>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane, ro + n, x4, p.prec);
               } else {
                 if (!p.first_layer) {
                   const uint4 o = op[pp];
@@ -447,10 +448,10 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 if (p.addend != nullptr) { y[0] += ad[k].x; y[1] += ad[k].y; y[2] += ad[k].z; y[3] += ad[k].w; }
                 if (p.res_f32 != nullptr) { y[0] += rs[k].x; y[1] += rs[k].y; y[2] += rs[k].z; y[3] += rs[k].w; }
                 if (p.res_planes != nullptr) {
-                  y[0] += fd_combine((uint16_t)(rh[k].x & 0xffff), (uint16_t)(rl[k].x & 0xffff), p.prec);
-                  y[1] += fd_combine((uint16_t)(rh[k].x >> 16), (uint16_t)(rl[k].x >> 16), p.prec);
-                  y[2] += fd_combine((uint16_t)(rh[k].y & 0xffff), (uint16_t)(rl[k].y & 0xffff), p.prec);
-                  y[3] += fd_combine((uint16_t)(rh[k].y >> 16), (uint16_t)(rl[k].y >> 16), p.prec);
+                  y[0] += p.res_scale * fd_combine((uint16_t)(rh[k].x & 0xffff), (uint16_t)(rl[k].x & 0xffff), p.prec);
+                  y[1] += p.res_scale * fd_combine((uint16_t)(rh[k].x >> 16), (uint16_t)(rl[k].x >> 16), p.prec);
+                  y[2] += p.res_scale * fd_combine((uint16_t)(rh[k].y & 0xffff), (uint16_t)(rl[k].y & 0xffff), p.prec);
+                  y[3] += p.res_scale * fd_combine((uint16_t)(rh[k].y >> 16), (uint16_t)(rl[k].y >> 16), p.prec);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) y[i] *= p.post_scale;

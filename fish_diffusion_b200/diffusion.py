@@ -250,23 +250,25 @@ class GaussianDiffusion(nn.Module):
             return loss_fn(noise, epsilon)
         raise NotImplementedError()
 
-    @torch.no_grad()
     def train_step(self, features, mel, x_masks=None, cond_masks=None, t=None, noise=None):
-        """Forward half of the reference train_step / p_losses (diffusion.py:129-190): t ~ U{0..N-1}[B],
-        x_t = q_sample(norm_spec(mel)), eps = denoise_fn(x_t, t, cond) (no masks), masked loss.
-        `t` / `noise` ([B,M,T]) may be injected for parity tests.  The backward through the native denoiser is not
-        implemented yet (see WaveNet.forward), so `loss` carries no graph."""
+        """Reference train_step / p_losses (diffusion.py:129-190): t ~ U{0..N-1}[B], x_t = q_sample(norm_spec(mel)),
+        eps = denoise_fn(x_t, t, cond) (no masks), masked loss.  `t` / `noise` ([B,M,T]) may be
+        injected for parity tests.  With grad enabled the loss carries the autograd graph through the native
+        forward/backward kernels (WaveNetTrainFn); under no_grad only the forward runs."""
         B, T, E = features.shape
         dev = features.device
         prec = self._prec()
         if t is None:
             t = torch.randint(0, self.num_timesteps, (B,), device=dev).long()
-        x = self.norm_spec(mel.to(torch.float32))                       # [B,T,M] channels-last
-        noise_cl = self._randn(tuple(x.shape), dev) if noise is None else self._to_cl(noise)
-        noised = self.q_sample(x, t, noise_cl)
-        cmask = None
-        cond_planes = N.split_nwc(features.to(torch.float32), prec, mask=cmask)
-        eps = self.denoise_fn.forward_cl(N.split_nwc(noised, prec), t.to(torch.float32), cond_planes)
+        with torch.no_grad():
+            x = self.norm_spec(mel.to(torch.float32))                   # [B,T,M] channels-last
+            noise_cl = self._randn(tuple(x.shape), dev) if noise is None else self._to_cl(noise)
+            noised = self.q_sample(x, t, noise_cl)
+        if torch.is_grad_enabled():
+            eps = self.denoise_fn.forward_train_cl(noised, t.to(torch.float32), features.to(torch.float32))
+        else:
+            cond_planes = N.split_nwc(features.to(torch.float32), prec)
+            eps = self.denoise_fn.forward_cl(N.split_nwc(noised, prec), t.to(torch.float32), cond_planes)
         if x_masks is not None:
             m = x_masks[:, :, None]
             noised = noised.masked_fill(m, 0.0)

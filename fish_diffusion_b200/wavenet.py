@@ -139,7 +139,7 @@ class WaveNet(nn.Module):
             s = N.pow2_scale(w2d)
             return N.pack_weight(w2d, prec, s), 1.0 / s
 
-        pk = {"prec": prec, "gate_tile": gate_tile, "backend": self._resolve_backend()}
+        pk = {"prec": prec, "gate_tile": gate_tile, "backend": self._resolve_backend(), "perm": perm}
         pk["w_in"], pk["w_in_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0])
         pk["b_in"] = f32(self.input_projection.conv.bias).contiguous()
         pk["mlp_w0"] = f32(self.mlp[0].linear.weight).contiguous()
@@ -192,6 +192,50 @@ class WaveNet(nn.Module):
             }
             self._ws = {key: ws}   # keep one shape resident
         return ws
+
+    # ------------------------------------------------------------------------------------ training path
+    def train_param_list(self):
+        """Conv parameters handed to WaveNetTrainFn, in the order of train_param_keys()."""
+        ps = [self.input_projection.conv.weight, self.input_projection.conv.bias]
+        for blk in self.residual_layers:
+            ps += [blk.conv_layer.conv.weight, blk.conv_layer.conv.bias, blk.conditioner_projection.conv.weight,
+                   blk.conditioner_projection.conv.bias, blk.output_projection.conv.weight,
+                   blk.output_projection.conv.bias]
+        ps += [self.skip_projection.conv.weight, self.skip_projection.conv.bias, self.output_projection.conv.weight,
+               self.output_projection.conv.bias]
+        return ps
+
+    def train_param_keys(self):
+        keys = [("w1x1", "input_projection.w"), ("b", "input_projection.b")]
+        for l in range(self.n_layers):
+            keys += [("w3", f"l{l}.w1"), ("b", f"l{l}.b1"), ("w1x1", f"l{l}.wc"), ("b", f"l{l}.b1"),
+                     ("w1x1", f"l{l}.w2"), ("b", f"l{l}.b2")]
+        keys += [("w1x1", "skip_projection.w"), ("b", "skip_projection.b"), ("w1x1", "output_projection.w"),
+                 ("b", "output_projection.b")]
+        return keys
+
+    def step_vectors(self, diffusion_step):
+        """d [Bs, L, C]: DiffusionEmbedding -> mlp -> per-layer diffusion_projection (wavenet.py:20-27,170-174,107)
+        with ordinary torch ops on [Bs, C]-sized tensors, so autograd covers these (tiny) parameters."""
+        import torch.nn.functional as F
+        C = self.residual_channels
+        half = C // 2
+        emb = math.log(10000) / (half - 1)
+        emb = torch.exp(torch.arange(half, device=diffusion_step.device) * -emb)
+        emb = diffusion_step[:, None] * emb[None, :]
+        s = torch.cat((emb.sin(), emb.cos()), dim=-1)
+        s = self.mlp[0].linear(s)
+        s = s * torch.tanh(F.softplus(s))
+        s = self.mlp[2].linear(s)
+        return torch.stack([blk.diffusion_projection.linear(s) for blk in self.residual_layers], dim=1)
+
+    def forward_train_cl(self, x_cl, diffusion_step, cond_cl):
+        """Differentiable channels-last forward: x_cl [B,T,M], diffusion_step [B] or [1], cond_cl [B,T,E] -> eps [B,T,M].
+        Gradients flow to every parameter, to cond_cl and (through d) to the step-embedding path.  No masks: the
+        reference trains without them (diffusion.py:134)."""
+        from .wavenet_train import WaveNetTrainFn
+        d = self.step_vectors(diffusion_step)
+        return WaveNetTrainFn.apply(self, x_cl.contiguous(), cond_cl.contiguous(), d, *self.train_param_list())
 
     # ------------------------------------------------------------------------------------ native forward
     @torch.no_grad()
@@ -248,12 +292,13 @@ class WaveNet(nn.Module):
     def forward(self, x, diffusion_step, conditioner, x_masks=None, cond_masks=None):
         """Reference contract (wavenet.py:194-236): x [B,M,T] (or [B,1,M,T]), diffusion_step [B] or [1] (int64 or
         float), conditioner [B,E,T], masks [B,T] bool -> [B,M,T] (4-D in -> 4-D out)."""
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # the backward (dgrad/wgrad tap-GEMMs) is the next row of the build plan; refuse rather than
-            # silently return a tensor that is detached from the graph
-            raise NotImplementedError(
-                "fish_diffusion_b200.WaveNet: autograd through the native kernels is not implemented yet; "
-                "call under torch.no_grad() (inference / sampling)")
+        if torch.is_grad_enabled() and (x.requires_grad or conditioner.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            if x_masks is not None or cond_masks is not None:
+                raise NotImplementedError("the differentiable path takes no masks (the reference trains without them)")
+            x3 = x[:, 0] if x.dim() == 4 else x
+            eps = self.forward_train_cl(x3.transpose(1, 2), diffusion_step, conditioner.transpose(1, 2)).transpose(1, 2)
+            return eps[:, None] if x.dim() == 4 else eps
         use_4_dim = x.dim() == 4
         if use_4_dim:
             x = x[:, 0]

@@ -1,0 +1,237 @@
+"""Training path of the native WaveNet: forward that keeps what the backward needs, and a hand-derived backward
+built from the same tap-GEMM kernels (reference: autograd through fish_diffusion/modules/wavenet.py:106-120,194-236
+inside GaussianDiffusion.p_losses, diffusion.py:129-151).
+
+Per residual block the backward is 6 GEMM-class launches (2x the forward FLOPs):
+  dz      = [dx_next/sqrt2 | d_skip] . W2            data gradient of the output projection  (K = 2C)
+  dW2     = [dx_next/sqrt2 | d_skip]^T . z           weight gradient (2 launches, K = time)
+  dW1     = dy^T . [x(t-d)+d, x(t)+d, x(t+d)+d, cond] weight gradient (4 launches: 3 taps + conditioner)
+  dx      = sum_tap dy(t -/+ d) . W1_tap + dx_next/sqrt2   data gradient of the dilated conv (K = 6C)
+  dcond  += dy . Wc
+Weight gradients run on folded transposes [channels][B][Tp] (fd_fold_transpose) so that time is the contraction axis of
+the same K-major tensor-core kernel; the tap shift becomes a K offset of the second operand and the zero padding of the
+conv is the zero padding between items.  The tiny step-embedding MLP / diffusion projections stay under torch autograd
+(they act on [B or 1, C] vectors); their output d enters the block through the gate-bias tables.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _native as N
+
+
+def _backend_for(pref, n_total, k_seg, num_seg):
+    if pref == N.BACKEND_TC and N.tc_supported_linear(n_total, k_seg, num_seg):
+        return N.BACKEND_TC
+    return N.BACKEND_SIMT
+
+
+def _pack(w2d, prec):
+    s = N.pow2_scale(w2d)
+    return N.pack_weight(w2d.contiguous(), prec, s), 1.0 / s
+
+
+class WaveNetTrainFn(torch.autograd.Function):
+    """eps_cl = f(x_cl [B,T,M], cond_cl [B,T,E], d [Bs,L,C], *conv weights);  see WaveNet.train_param_list()."""
+
+    @staticmethod
+    def forward(ctx, net, x_cl, cond_cl, d, *weights):
+        dev = x_cl.device
+        N.require_cuda(x_cl, "x")
+        B, T, M = x_cl.shape
+        C, E, L = net.residual_channels, net.d_encoder, net.n_layers
+        Bs = d.shape[0]
+        pk = net._packed(dev)                       # forward packs (re-made whenever a parameter version changes)
+        prec, backend = pk["prec"], pk["backend"]
+        lib, st = N.lib(), N.stream_ptr(dev)
+        i16 = dict(dtype=torch.int16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        x_planes = N.split_nwc(x_cl.detach().to(torch.float32), prec)
+        cond_planes = N.split_nwc(cond_cl.detach().to(torch.float32), prec)
+        d = d.detach().to(torch.float32).contiguous()
+        gb = torch.empty((3, L, Bs, 2 * C), **f32)
+        N.check(lib.fd_wavenet_gate_bias_from_d(N.ptr(d), N.ptr(pk["w1p_f32"]), N.ptr(pk["bias_sum"]), N.ptr(gb[0]),
+                                                N.ptr(gb[1]), N.ptr(gb[2]), L, Bs, C, 3 * C + E, st),
+                "fd_wavenet_gate_bias_from_d")
+        xs = [torch.empty((2, B, T, C), **i16) for _ in range(L + 1)]    # residual stream entering each layer
+        ys = [torch.empty((2, B, T, 2 * C), **i16) for _ in range(L)]    # gate/filter pre-activations (packed order)
+        z = torch.empty((2, B, T, C), **i16)
+        skip_f32 = torch.empty((B, T, C), **f32)
+        s_planes = torch.empty((2, B, T, C), **i16)
+        h_planes = torch.empty((2, B, T, C), **i16)
+        eps = torch.empty((B, T, M), **f32)
+        N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], out_planes=xs[0], w_inv_scale=pk["w_in_inv"],
+                  act=N.ACT_RELU, prec=prec, backend=backend)
+        gb_stride = 2 * C if Bs > 1 else 0
+        for l in range(L):
+            flags = (1 if l == 0 else 0) | (2 if l == L - 1 else 0)
+            N.check(lib.fd_wavenet_block_fwd_train(
+                N.ptr(xs[l]), N.ptr(xs[l + 1]), N.ptr(cond_planes), N.ptr(z), N.ptr(ys[l]), N.ptr(pk["w1"][l]),
+                N.ptr(pk["w2"][l]), N.ptr(gb[0, l]), N.ptr(gb[1, l]), N.ptr(gb[2, l]), gb_stride, N.ptr(pk["b2"][l]),
+                N.ptr(skip_f32), N.ptr(s_planes), 1.0 / math.sqrt(L), B, T, C, E, pk["dil"][l], pk["gate_tile"],
+                pk["w1_inv"][l], pk["w2_inv"][l], flags, prec, backend, st), "fd_wavenet_block_fwd_train")
+        N.conv_cl(s_planes, pk["w_skip"], B, T, C, C, [0], bias=pk["b_skip"], out_planes=h_planes,
+                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=prec, backend=backend)
+        N.conv_cl(h_planes, pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], out_f32=eps, w_inv_scale=pk["w_out_inv"],
+                  prec=prec, backend=backend)
+        ctx.net = net
+        ctx.saved = dict(x_planes=x_planes, cond_planes=cond_planes, d=d, xs=xs, ys=ys, s_planes=s_planes,
+                         h_planes=h_planes, shape=(B, T, M, Bs))
+        ctx.need_cond = cond_cl.requires_grad
+        return eps
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        net, sv = ctx.net, ctx.saved
+        B, T, M, Bs = sv["shape"]
+        C, E, L = net.residual_channels, net.d_encoder, net.n_layers
+        dev = d_eps.device
+        pk = net._packed(dev)
+        prec, pref = pk["prec"], pk["backend"]
+        perm, half, gate_tile = pk["perm"], pk["gate_tile"] // 2, pk["gate_tile"]
+        lib, st = N.lib(), N.stream_ptr(dev)
+        i16 = dict(dtype=torch.int16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        inv_sqrt2, inv_sqrtL = 1.0 / math.sqrt(2.0), 1.0 / math.sqrt(L)
+        PAD = max(pk["dil"])
+        Tp = (T + 2 * PAD + 63) // 64 * 64
+        rows = B * T
+
+        # ---------------------------------------------------------------- helpers
+        def fold(planes, Cc, mode=0, scale=1.0, src_f32=None, aux=None, addvec=None, add_bstride=0):
+            out = torch.empty((2, Cc, B, Tp), **i16)
+            N.check(lib.fd_fold_transpose(N.ptr(planes), N.ptr(src_f32), N.ptr(aux), N.ptr(addvec), add_bstride,
+                                          N.ptr(out), B, T, Cc, Tp, PAD, scale, mode, gate_tile, prec, st),
+                    "fd_fold_transpose")
+            return out
+
+        def wgrad(rowsT, R, colsT, Cc, shift=0):
+            """sum_{b,t} rows[b,t,r] * cols[b,t+shift,c]  -> fp32 [R, Cc]"""
+            part = torch.empty((B, R, Cc), **f32)
+            N.gemm_cl(rowsT, Tp, colsT, Cc, B * Tp, B, R, [(0, 0, 0, Tp)], strides0=(B * Tp, Tp, R * B * Tp),
+                      w_kshift=shift, w_bstride_k=Tp, out_f32=part, prec=prec,
+                      backend=_backend_for(pref, Cc, Tp, 1))
+            out = torch.empty((R, Cc), **f32)
+            N.check(lib.fd_reduce_batch(N.ptr(part), N.ptr(out), B, R * Cc, 1.0, st), "fd_reduce_batch")
+            return out
+
+        def colsum(planes=None, f32t=None, Nn=0, scale=1.0):
+            out = torch.zeros((B, Nn), **f32)
+            N.check(lib.fd_colsum(N.ptr(planes), N.ptr(f32t), N.ptr(out), B, T, Nn, scale, prec, st), "fd_colsum")
+            return out
+
+        def dgrad(src0, C0, w, w_inv, n_total, k_total, segs, **kw):
+            k_seg = segs[0][3]
+            N.gemm_cl(src0, C0, w, n_total, k_total, B, T, segs, w_inv_scale=w_inv, prec=prec,
+                      backend=_backend_for(pref, n_total, k_seg, len(segs)), **kw)
+
+        g = lambda name: getattr(net, name)
+        grads = {}
+
+        # ---------------------------------------------------------------- tail (wavenet.py:229-231)
+        de = d_eps.detach().to(torch.float32).contiguous()
+        de_planes = N.split_nwc(de, prec)
+        deT = fold(de_planes, M)
+        hT = fold(sv["h_planes"], C)
+        grads["output_projection.w"] = wgrad(deT, M, hT, C)                       # [M, C]
+        grads["output_projection.b"] = colsum(f32t=de, Nn=M).sum(0)
+        WoT, WoT_inv = _pack(g("output_projection").conv.weight.detach()[:, :, 0].t().to(torch.float32), prec)
+        dh_raw = torch.empty((B, T, C), **f32)
+        dgrad(de_planes, M, WoT, WoT_inv, C, M, [(0, 0, 0, M)], out_f32=dh_raw)
+        dh_planes = torch.empty((2, B, T, C), **i16)
+        N.check(lib.fd_relu_bwd(N.ptr(dh_raw), N.ptr(sv["h_planes"]), N.ptr(dh_planes), rows * C, 1.0, prec, st),
+                "fd_relu_bwd")
+        dhT = fold(dh_planes, C)
+        sT = fold(sv["s_planes"], C)
+        grads["skip_projection.w"] = wgrad(dhT, C, sT, C)
+        grads["skip_projection.b"] = colsum(planes=dh_planes, Nn=C).sum(0)
+        WsT, WsT_inv = _pack(g("skip_projection").conv.weight.detach()[:, :, 0].t().to(torch.float32), prec)
+        dskip_planes = torch.empty((2, B, T, C), **i16)                           # d(skip_l) = ds / sqrt(L), every layer
+        dgrad(dh_planes, C, WsT, WsT_inv, C, C, [(0, 0, 0, C)], out_planes=dskip_planes, planes_scale=inv_sqrtL)
+        dskipT = fold(dskip_planes, C)
+        cs_skip = colsum(planes=dskip_planes, Nn=C)                              # [B, C]
+        condT = fold(sv["cond_planes"], E)
+        d_cond = torch.zeros((B, T, E), **f32) if ctx.need_cond else None
+
+        # ---------------------------------------------------------------- residual blocks, last to first
+        dx_next = None            # planes of d(x_{l+1}); None above the last layer (its residual output is unused)
+        cs_next = None            # column sums of dx_next per item
+        d_d = torch.zeros((Bs, L, C), **f32)
+        dz = torch.empty((B, T, C), **f32)
+        dx0 = torch.empty((B, T, C), **f32)       # fp32 copy of d(x_0), written by the layer-0 data gradient
+        for l in reversed(range(L)):
+            blk = net.residual_layers[l]
+            dil = pk["dil"][l]
+            W2 = blk.output_projection.conv.weight.detach()[:, :, 0].to(torch.float32)          # [2C, C]
+            W2T = W2.t().clone()                                                                 # [C, 2C]
+            W2T[:, :C] *= inv_sqrt2                                                              # residual half: /sqrt2
+            W2Tp, W2T_inv = _pack(W2T, prec)
+            if dx_next is None:
+                N.gemm_cl(dskip_planes, C, W2Tp, C, 2 * C, B, T, [(0, 0, 0, C)], w_kshift=C, out_f32=dz,
+                          w_inv_scale=W2T_inv, prec=prec, backend=_backend_for(pref, C, C, 1))
+            else:
+                N.gemm_cl(dx_next, C, W2Tp, C, 2 * C, B, T, [(0, 0, 0, C), (1, 0, 0, C)], src1=dskip_planes, C1=C,
+                          out_f32=dz, w_inv_scale=W2T_inv, prec=prec, backend=_backend_for(pref, C, C, 2))
+            dy = torch.empty((2, B, T, 2 * C), **i16)
+            N.check(lib.fd_gate_bwd(N.ptr(dz), N.ptr(sv["ys"][l]), N.ptr(dy), rows, C, gate_tile, prec, st), "fd_gate_bwd")
+            # ---- weight gradients of the output projection: rows [residual | skip] x z
+            zT = fold(sv["ys"][l], C, mode=1)
+            gw2 = torch.empty((2 * C, C), **f32)
+            gb2 = torch.empty((2 * C,), **f32)
+            if dx_next is None:
+                gw2[:C].zero_(); gb2[:C].zero_()
+            else:
+                dxnT = fold(dx_next, C, scale=inv_sqrt2)
+                gw2[:C] = wgrad(dxnT, C, zT, C)
+                gb2[:C] = cs_next.sum(0) * inv_sqrt2
+            gw2[C:] = wgrad(dskipT, C, zT, C)
+            gb2[C:] = cs_skip.sum(0)
+            grads[f"l{l}.w2"], grads[f"l{l}.b2"] = gw2, gb2
+            # ---- weight gradients of the dilated conv + conditioner projection (packed row order -> original)
+            dyT = fold(dy, 2 * C)
+            addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
+            xdT = fold(sv["xs"][l], C, addvec=addvec, add_bstride=C if Bs > 1 else 0)
+            gw1 = torch.empty((2 * C, C, 3), **f32)
+            for j, sh in enumerate((-dil, 0, dil)):
+                gw1[perm, :, j] = wgrad(dyT, 2 * C, xdT, C, shift=sh)
+            gwc = torch.empty((2 * C, E), **f32)
+            gwc[perm] = wgrad(dyT, 2 * C, condT, E)
+            gb1 = torch.empty((2 * C,), **f32)
+            gb1[perm] = colsum(planes=dy, Nn=2 * C).sum(0)
+            grads[f"l{l}.w1"], grads[f"l{l}.wc"], grads[f"l{l}.b1"] = gw1, gwc, gb1
+            # ---- data gradients: dx_l = conv^T(dy) + dx_next/sqrt2 ;  dcond += dy . Wc
+            Wc = blk.conv_layer.conv.weight.detach().to(torch.float32)                # [2C, C, 3]
+            W1T = torch.cat([Wc[perm, :, j].t() for j in range(3)], dim=1)            # [C, 3*2C], packed dy order
+            W1Tp, W1T_inv = _pack(W1T, prec)
+            dx_l = torch.empty((2, B, T, C), **i16)
+            dgrad(dy, 2 * C, W1Tp, W1T_inv, C, 6 * C, [(0, dil, 0, 2 * C), (0, 0, 0, 2 * C), (0, -dil, 0, 2 * C)],
+                  res_planes=dx_next, res_scale=inv_sqrt2, out_planes=dx_l, out_f32=dx0 if l == 0 else None)
+            if d_cond is not None:
+                WcT, WcT_inv = _pack(blk.conditioner_projection.conv.weight.detach()[perm, :, 0].t().to(torch.float32),
+                                     prec)
+                dgrad(dy, 2 * C, WcT, WcT_inv, E, 2 * C, [(0, 0, 0, 2 * C)], out_f32=d_cond, out_accum=True)
+            cs_l = colsum(planes=dx_l, Nn=C)
+            dd = cs_l if cs_next is None else cs_l - cs_next * inv_sqrt2               # d wrt the step vector d_l
+            d_d[:, l, :] = dd if Bs > 1 else dd.sum(0, keepdim=True)
+            dx_next, cs_next = dx_l, cs_l
+
+        # ---------------------------------------------------------------- head (wavenet.py:211-212)
+        # dx_next now is d(x_0) where x_0 = relu(input_projection(x)): mask with x_0 > 0
+        dx0m = torch.empty((2, B, T, C), **i16)
+        N.check(lib.fd_relu_bwd(N.ptr(dx0), N.ptr(sv["xs"][0]), N.ptr(dx0m), rows * C, 1.0, prec, st), "fd_relu_bwd")
+        dx0mT = fold(dx0m, C)
+        xnT = fold(sv["x_planes"], M)
+        grads["input_projection.w"] = wgrad(dx0mT, C, xnT, M)
+        grads["input_projection.b"] = colsum(planes=dx0m, Nn=C).sum(0)
+
+        out = [None, None, d_cond, d_d]
+        for kind, key in net.train_param_keys():
+            gr = grads[key]
+            if kind == "w1x1":
+                gr = gr[:, :, None]
+            out.append(gr)
+        ctx.saved = None
+        return tuple(out)

@@ -166,6 +166,66 @@ int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag
 /* log(clamp(x, clip)) * out_scale over fp32 (audio.py:11-18 dynamic_range_compression) */
 int fd_log_clamp(const float* x, float* y, long long n, float clip, float out_scale, void* stream);
 
+/* ------------------------------------------------------------------ training step (a8): backward of the denoiser */
+/* General linear tap-GEMM: up to two source tensors, explicit source strides (0 = canonical [2][B][T][C]), a K offset
+ * on the W operand (w_kshift + b*w_bstride_k).  It expresses every gradient GEMM of the WaveNet backward:
+ *   data gradients: transposed packed weights, mirrored tap shifts, two sources ([dx_next | d_skip]);
+ *   weight gradients: src = folded transpose of the output gradient ("rows" = output channels, C = padded time),
+ *                     W = folded transpose of the forward input, w_kshift = tap shift, w_bstride_k = Tp,
+ *                     out_f32 [B][rows][cols] holds one partial per batch item (reduced by fd_reduce_batch).
+ * Epilogue = the LINEAR epilogue of fd_conv_cl_fwd plus res_scale on the res_planes term. */
+typedef struct fd_gemm_desc {
+  const uint16_t* src[2];
+  int src_C[2];
+  long long src_rs[2], src_bs[2], src_ps[2];
+  const uint16_t* w;
+  int n_total, k_total, w_kshift;
+  long long w_bstride_k;
+  int B, T, num_seg;
+  int seg_src[16], seg_shift[16], seg_coff[16], seg_klen[16];
+  const float* bias;
+  const float* addend;
+  const float* res_f32;
+  const uint16_t* res_planes;
+  const uint8_t* row_mask;
+  float* out_f32;
+  uint16_t* out_planes;
+  float w_inv_scale, res_scale, post_scale, planes_scale, act_slope;
+  int out_accum, act, prec, backend;
+} fd_gemm_desc;
+int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream);
+
+/* fd_wavenet_block_fwd for training: the updated residual stream goes to x_out_planes (x_planes stays intact, it is
+ * needed by the weight gradient) and the gate/filter pre-activations are kept in y_planes [2][B][T][2C] (packed order). */
+int fd_wavenet_block_fwd_train(const uint16_t* x_planes, uint16_t* x_out_planes, const uint16_t* cond_planes,
+                               uint16_t* z_planes, uint16_t* y_planes, const uint16_t* w1, const uint16_t* w2,
+                               const float* gb_full, const float* gb_lo, const float* gb_hi, int gb_bstride,
+                               const float* b2, float* skip_f32, uint16_t* skip_planes, float skip_scale, int B, int T,
+                               int C, int E, int dilation, int gate_tile, float w1_inv_scale, float w2_inv_scale,
+                               int flags, int prec, int backend, void* stream);
+/* gate-bias tables from already projected step vectors d [Bs][L][C] (training: the embedding MLP and the
+ * diffusion projections run under torch autograd on [Bs,C]-sized tensors) */
+int fd_wavenet_gate_bias_from_d(const float* d, const float* w1p, const float* bias_sum, float* gb_full, float* gb_lo,
+                                float* gb_hi, int L, int Bs, int C, int KT, void* stream);
+/* planes [2][B][T][C] -> planes [2][C][B][Tp] (item b at columns [pad, pad+T) of its Tp span, zeros elsewhere).
+ * mode 0: value*scale (+ addvec[b*add_bstride + c]); mode 1: src is a packed pre-activation tensor with 2C columns,
+ * value = sigmoid(g)*tanh(f); mode 2: value = src_f32 * (aux_planes > 0) (ReLU backward). */
+int fd_fold_transpose(const uint16_t* src_planes, const float* src_f32, const uint16_t* aux_planes, const float* addvec,
+                      int add_bstride, uint16_t* dst, int B, int T, int C, int Tp, int pad, float scale, int mode,
+                      int gate_tile, int prec, void* stream);
+/* backward of z = sigmoid(g)*tanh(f) (wavenet.py:114-115): dz fp32 [rows][C], y planes [2][rows][2C] -> dy planes */
+int fd_gate_bwd(const float* dz, const uint16_t* y_planes, uint16_t* dy_planes, long long rows, int C, int gate_tile,
+                int prec, void* stream);
+/* out planes = split(grad * (act_planes > 0) * scale) (ReLU backward, wavenet.py:212,230) */
+int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_planes, long long n, float scale, int prec,
+                void* stream);
+/* out[b][n] += scale * sum_t in[b,t,n]  (bias / step-vector gradients); exactly one of planes / f32 is non-NULL;
+ * out must be zero-initialised by the caller */
+int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T, int N, float scale, int prec,
+              void* stream);
+/* out[i] = scale * sum_b in[b][i]  (reduction of the per-item weight-gradient partials) */
+int fd_reduce_batch(const float* in, float* out, int B, long long n, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -300,12 +300,40 @@ def gold_mel(ref, out):
     out["mel_fb_torchaudio"] = fb.astype(np.float32)
 
 
+def gold_train(ref, out):
+    """Gradients of GaussianDiffusion.p_losses (smoothed-l1) through the reference WaveNet via torch autograd:
+    every denoiser parameter and the conditioner, for per-item steps t[B] (training) -- the pin for the native
+    backward kernels."""
+    for name, cfg, seed, B, T in (("small", WN_SMALL, 51, 2, 40), ("tc", WN_TC, 52, 2, 200)):
+        M, E = cfg["mel_channels"], cfg["d_encoder"]
+        sd = wn_weights(seed, cfg)
+        diff = ref.diffusion.GaussianDiffusion(
+            denoiser=dict(type="WaveNetDenoiser", **cfg), mel_channels=M, noise_loss="smoothed-l1", sampler_interval=10,
+            spec_min=[-5.0], spec_max=[0.0])
+        diff.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        rng = np.random.RandomState(seed + 1)
+        feats = torch.from_numpy(rng.randn(B, T, E).astype(np.float32)).requires_grad_(True)
+        mel = (rng.rand(B, T, M).astype(np.float32) * 5 - 5)
+        t = torch.tensor([7, 642][:B], dtype=torch.long)
+        noise = rng.randn(B, M, T).astype(np.float32)
+        x = diff.norm_spec(torch.from_numpy(mel)).transpose(1, 2)
+        noised, eps, loss = diff.p_losses(x, t, feats.transpose(1, 2), noise=torch.from_numpy(noise))
+        loss.backward()
+        out[f"train_{name}_features"], out[f"train_{name}_mel"] = feats.detach().numpy(), mel
+        out[f"train_{name}_t"], out[f"train_{name}_noise"] = t.numpy(), noise
+        out[f"train_{name}_loss"] = loss.detach().numpy()
+        out[f"train_{name}_eps"] = eps.detach().numpy()
+        out[f"train_{name}_gfeatures"] = feats.grad.numpy()
+        for k, p in diff.denoise_fn.named_parameters():
+            out[f"train_{name}_g_{k}"] = p.grad.numpy()
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = load_reference()
     groups = {"schedules": gold_schedules, "wavenet": gold_wavenet, "sampler": gold_sampler, "vocoder": gold_vocoder,
-              "mel": gold_mel}
+              "mel": gold_mel, "train": gold_train}
     only = sys.argv[1:]
     for name, fn in groups.items():
         if only and name not in only:
