@@ -100,11 +100,20 @@ class WaveNetTrainFn(torch.autograd.Function):
         Tp = (T + 2 * PAD + 63) // 64 * 64
         rows = B * T
 
+        # Gradient scaling: loss gradients are ~1/numel (1e-6 and below at training shapes), under the fp16 plane
+        # range.  The whole backward chain therefore runs on S * gradient with S a power of two that puts
+        # max|d_eps| into [32, 64); every quantity that leaves the chain (weight / bias / conditioner / step-vector
+        # gradients) is multiplied by 1/S exactly.  One host sync per backward to read max|d_eps|.
+        amax = float(d_eps.detach().abs().max())
+        S = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** math.floor(math.log2(64.0 / amax))
+        inv_S = 1.0 / S
+
         # ---------------------------------------------------------------- helpers
-        def fold(planes, Cc, mode=0, scale=1.0, src_f32=None, aux=None, addvec=None, add_bstride=0):
+        def fold(planes, Cc, mode=0, scale=1.0, src_f32=None, aux=None, addvec=None, add_bstride=0, pad=None):
             out = torch.empty((2, Cc, B, Tp), **i16)
             N.check(lib.fd_fold_transpose(N.ptr(planes), N.ptr(src_f32), N.ptr(aux), N.ptr(addvec), add_bstride,
-                                          N.ptr(out), B, T, Cc, Tp, PAD, scale, mode, gate_tile, prec, st),
+                                          N.ptr(out), B, T, Cc, Tp, PAD if pad is None else pad, scale, mode, gate_tile,
+                                          prec, st),
                     "fd_fold_transpose")
             return out
 
@@ -115,12 +124,14 @@ class WaveNetTrainFn(torch.autograd.Function):
                       w_kshift=shift, w_bstride_k=Tp, out_f32=part, prec=prec,
                       backend=_backend_for(pref, Cc, Tp, 1))
             out = torch.empty((R, Cc), **f32)
-            N.check(lib.fd_reduce_batch(N.ptr(part), N.ptr(out), B, R * Cc, 1.0, st), "fd_reduce_batch")
+            N.check(lib.fd_reduce_batch(N.ptr(part), N.ptr(out), B, R * Cc, inv_S, st), "fd_reduce_batch")
             return out
 
-        def colsum(planes=None, f32t=None, Nn=0, scale=1.0):
+        def colsum(planes=None, f32t=None, Nn=0):
+            # gradients stored in planes are S-scaled (see below); fp32 inputs are not
             out = torch.zeros((B, Nn), **f32)
-            N.check(lib.fd_colsum(N.ptr(planes), N.ptr(f32t), N.ptr(out), B, T, Nn, scale, prec, st), "fd_colsum")
+            N.check(lib.fd_colsum(N.ptr(planes), N.ptr(f32t), N.ptr(out), B, T, Nn, inv_S if planes is not None else 1.0,
+                                  prec, st), "fd_colsum")
             return out
 
         def dgrad(src0, C0, w, w_inv, n_total, k_total, segs, **kw):
@@ -133,7 +144,7 @@ class WaveNetTrainFn(torch.autograd.Function):
 
         # ---------------------------------------------------------------- tail (wavenet.py:229-231)
         de = d_eps.detach().to(torch.float32).contiguous()
-        de_planes = N.split_nwc(de, prec)
+        de_planes = N.split_nwc(de, prec, scale=S)
         deT = fold(de_planes, M)
         hT = fold(sv["h_planes"], C)
         grads["output_projection.w"] = wgrad(deT, M, hT, C)                       # [M, C]
@@ -193,10 +204,12 @@ class WaveNetTrainFn(torch.autograd.Function):
             # ---- weight gradients of the dilated conv + conditioner projection (packed row order -> original)
             dyT = fold(dy, 2 * C)
             addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
-            xdT = fold(sv["xs"][l], C, addvec=addvec, add_bstride=C if Bs > 1 else 0)
             gw1 = torch.empty((2 * C, C, 3), **f32)
             for j, sh in enumerate((-dil, 0, dil)):
-                gw1[perm, :, j] = wgrad(dyT, 2 * C, xdT, C, shift=sh)
+                # the tap shift is baked into the folded transpose (data starts at column PAD - shift): a TMA box must
+                # start on a 16-byte boundary, so an element-granular K offset on the operand is not an option
+                xdT = fold(sv["xs"][l], C, addvec=addvec, add_bstride=C if Bs > 1 else 0, pad=PAD - sh)
+                gw1[perm, :, j] = wgrad(dyT, 2 * C, xdT, C)
             gwc = torch.empty((2 * C, E), **f32)
             gwc[perm] = wgrad(dyT, 2 * C, condT, E)
             gb1 = torch.empty((2 * C,), **f32)
@@ -212,7 +225,7 @@ class WaveNetTrainFn(torch.autograd.Function):
             if d_cond is not None:
                 WcT, WcT_inv = _pack(blk.conditioner_projection.conv.weight.detach()[perm, :, 0].t().to(torch.float32),
                                      prec)
-                dgrad(dy, 2 * C, WcT, WcT_inv, E, 2 * C, [(0, 0, 0, 2 * C)], out_f32=d_cond, out_accum=True)
+                dgrad(dy, 2 * C, WcT, WcT_inv * inv_S, E, 2 * C, [(0, 0, 0, 2 * C)], out_f32=d_cond, out_accum=True)
             cs_l = colsum(planes=dx_l, Nn=C)
             dd = cs_l if cs_next is None else cs_l - cs_next * inv_sqrt2               # d wrt the step vector d_l
             d_d[:, l, :] = dd if Bs > 1 else dd.sum(0, keepdim=True)

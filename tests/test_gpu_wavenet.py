@@ -81,11 +81,23 @@ def test_wavenet_repacks_when_weights_change(golden_cfg):
     assert rel_l2(y2.cpu().numpy(), ref2) < 2e-5 and rel_l2(y1.cpu().numpy(), ref2) > 1e-2
 
 
-def test_autograd_is_refused_not_silently_detached(golden_cfg):
+def test_reference_layout_forward_is_differentiable(golden_cfg):
+    """WaveNet.forward([B,M,T]) with grad enabled goes through the native backward (never silently detached);
+    masks are refused there because the reference trains without them (diffusion.py:134)."""
     cfg = golden_cfg["WN_TC"]
     net = build_net(cfg, wn_weights(1, cfg))
+    x = torch.randn(1, 64, 20, device=dev())
+    c = torch.randn(1, 64, 20, device=dev(), requires_grad=True)
+    y = net(x, torch.tensor([1], device=dev()), c)
+    assert y.requires_grad and y.shape == (1, 64, 20)
+    y.square().mean().backward()
+    assert c.grad is not None and torch.isfinite(c.grad).all() and float(c.grad.abs().max()) > 0
+    assert net.input_projection.conv.weight.grad is not None
+    with torch.no_grad():
+        y0 = net(x, torch.tensor([1], device=dev()), c)
+    assert torch.allclose(y0, y.detach(), rtol=1e-5, atol=1e-6)      # training and inference forwards agree
     with pytest.raises(NotImplementedError):
-        net(torch.randn(1, 64, 20, device=dev()), torch.tensor([1], device=dev()), torch.randn(1, 64, 20, device=dev()))
+        net(x, torch.tensor([1], device=dev()), c, x_masks=torch.zeros(1, 20, dtype=torch.bool, device=dev()))
 
 
 # ------------------------------------------------------------------ samplers, noise injected
@@ -142,6 +154,7 @@ def test_train_step_forward_vs_reference(golden, golden_cfg):
     g = golden("sampler")
     diff = _build_diffusion(golden_cfg, "naive", 10)
     out = diff.train_step(T_(g["samp_features"]), T_(g["train_mel"]), t=T_(g["train_t"]), noise=T_(g["train_noise"]))
-    assert rel_l2(out["noised_mels"].cpu().numpy(), g["train_noised"]) < 1e-6
-    assert rel_l2(out["epsilon"].cpu().numpy(), g["train_eps"]) < 2e-5
+    assert out["loss"].requires_grad                      # grad mode: the loss carries the native backward
+    assert rel_l2(out["noised_mels"].detach().cpu().numpy(), g["train_noised"]) < 1e-6
+    assert rel_l2(out["epsilon"].detach().cpu().numpy(), g["train_eps"]) < 2e-5
     assert abs(float(out["loss"]) - float(g["train_loss"])) < 2e-5 * abs(float(g["train_loss"]))
