@@ -56,7 +56,7 @@ _SIGS = {
                                    [c_int] * 6 + [c_float, c_float, c_int, c_int, c_int, c_void_p]),
     "fd_wavenet_gate_bias_from_d": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
     "fd_fold_transpose": (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 5 + [c_float, c_int, c_int, c_int,
-                                                                                   c_void_p]),
+                                                                                   c_int, c_int, c_void_p]),
     "fd_gate_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_int, c_int, c_int, c_void_p]),
     "fd_relu_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_float, c_int, c_void_p]),
     "fd_colsum": (c_int, [c_void_p] * 3 + [c_int, c_int, c_int, c_float, c_int, c_void_p]),

@@ -15,7 +15,7 @@ template <int MODE>
 __global__ void k_fold_transpose(const uint16_t* __restrict__ src, const float* __restrict__ src_f32,
                                  const uint16_t* __restrict__ aux, const float* __restrict__ addvec, int add_bstride,
                                  uint16_t* __restrict__ dst, int B, int T, int C, int Tp, int pad, float scale,
-                                 int gate_tile, int prec) {
+                                 int gate_tile, int prec, int dst_rows, int dst_row0) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;   // t0 indexes the padded axis
@@ -47,13 +47,13 @@ __global__ void k_fold_transpose(const uint16_t* __restrict__ src, const float* 
     tile[i][threadIdx.x] = v;
   }
   __syncthreads();
-  const size_t dplane = (size_t)C * B * Tp;
+  const size_t dplane = (size_t)dst_rows * B * Tp;      // the destination may be a taller stacked operand
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, tp = t0 + threadIdx.x;
     if (c < C && tp < Tp) {
       uint16_t hi, lo;
       fd_split(tile[threadIdx.x][i], prec, hi, lo);
-      const size_t off = ((size_t)c * B + b) * Tp + tp;
+      const size_t off = ((size_t)(dst_row0 + c) * B + b) * Tp + tp;
       dst[off] = hi;
       dst[dplane + off] = lo;
     }
@@ -141,20 +141,23 @@ extern "C" {
 
 int fd_fold_transpose(const uint16_t* src_planes, const float* src_f32, const uint16_t* aux_planes, const float* addvec,
                       int add_bstride, uint16_t* dst, int B, int T, int C, int Tp, int pad, float scale, int mode,
-                      int gate_tile, int prec, void* stream) {
+                      int gate_tile, int prec, int dst_rows, int dst_row0, void* stream) {
   FD_REQUIRE(Tp >= T + pad && pad >= 0, "fd_fold_transpose: Tp=%d too small for T=%d pad=%d", Tp, T, pad);
+  if (dst_rows <= 0) { dst_rows = C; dst_row0 = 0; }
+  FD_REQUIRE(dst_row0 >= 0 && dst_row0 + C <= dst_rows, "fd_fold_transpose: rows [%d,%d) outside the %d-row destination",
+             dst_row0, dst_row0 + C, dst_rows);
   FD_REQUIRE(mode >= 0 && mode <= 2, "fd_fold_transpose: bad mode %d", mode);
   dim3 grid((Tp + 31) / 32, (C + 31) / 32, B), block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0)
     k_fold_transpose<0><<<grid, block, 0, st>>>(src_planes, nullptr, nullptr, addvec, add_bstride, dst, B, T, C, Tp, pad,
-                                                scale, gate_tile, prec);
+                                                scale, gate_tile, prec, dst_rows, dst_row0);
   else if (mode == 1)
     k_fold_transpose<1><<<grid, block, 0, st>>>(src_planes, nullptr, nullptr, nullptr, 0, dst, B, T, C, Tp, pad, scale,
-                                                gate_tile, prec);
+                                                gate_tile, prec, dst_rows, dst_row0);
   else
     k_fold_transpose<2><<<grid, block, 0, st>>>(nullptr, src_f32, aux_planes, nullptr, 0, dst, B, T, C, Tp, pad, scale,
-                                                gate_tile, prec);
+                                                gate_tile, prec, dst_rows, dst_row0);
   FD_LAUNCHED();
   return 0;
 }

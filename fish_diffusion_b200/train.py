@@ -25,7 +25,10 @@ class TrainStepModule(nn.Module):
 
 class DenoiserTrainer:
     def __init__(self, diffusion, lr=8e-4, weight_decay=1e-2, betas=(0.9, 0.98), eps=1e-9, clip=0.5,
-                 fp16_compress=True, device=None):
+                 fp16_compress=False, device=None):
+        """fp16_compress=True reproduces the reference's `ddp_comm_hook=fp16_compress_hook` (trainers/base.py:40).  It
+        is off by default here: over NVLink 5 the fp32 all-reduce of the 55 M gradients costs ~1.6 ms per step while
+        the hook's cast/divide passes cost ~10 ms (measured on 2xB200, profiles/r01_summary.md)."""
         self.diffusion = diffusion
         self.module = TrainStepModule(diffusion)
         self.ddp = None

@@ -135,28 +135,41 @@ class WaveNet(nn.Module):
         idx = torch.arange(C, device=device).view(C // half, half)
         perm = torch.cat([idx, idx + C], dim=1).reshape(-1)
 
-        def pack(w2d):
-            s = N.pow2_scale(w2d)
-            return N.pack_weight(w2d, prec, s), 1.0 / s
+        # power-of-two prescales of every packed matrix from ONE device->host transfer (training repacks every step)
+        raw = [self.input_projection.conv.weight, self.skip_projection.conv.weight, self.output_projection.conv.weight]
+        for blk in self.residual_layers:
+            raw += [blk.conv_layer.conv.weight, blk.conditioner_projection.conv.weight, blk.output_projection.conv.weight]
+        amax = torch.stack(torch._foreach_norm([w.detach() for w in raw], float("inf"))).tolist()
 
-        pk = {"prec": prec, "gate_tile": gate_tile, "backend": self._resolve_backend(), "perm": perm}
-        pk["w_in"], pk["w_in_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0])
+        def p2(m):
+            return 1.0 if m == 0.0 or m != m else float(2.0 ** math.floor(math.log2(64.0 / m)))
+
+        s_in, s_skip, s_out = p2(amax[0]), p2(amax[1]), p2(amax[2])
+        s1 = [p2(max(amax[3 + 3 * l], amax[4 + 3 * l])) for l in range(L)]
+        s2 = [p2(amax[5 + 3 * l]) for l in range(L)]
+
+        def pack(w2d, sc):
+            return N.pack_weight(w2d, prec, sc), 1.0 / sc
+
+        pk = {"prec": prec, "gate_tile": gate_tile, "backend": self._resolve_backend(), "perm": perm,
+              "s_in": s_in, "s_skip": s_skip, "s_out": s_out, "s1": s1, "s2": s2}
+        pk["w_in"], pk["w_in_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0], s_in)
         pk["b_in"] = f32(self.input_projection.conv.bias).contiguous()
         pk["mlp_w0"] = f32(self.mlp[0].linear.weight).contiguous()
         pk["mlp_b0"] = f32(self.mlp[0].linear.bias).contiguous() if self.mlp[0].linear.bias is not None else None
         pk["mlp_w1"] = f32(self.mlp[2].linear.weight).contiguous()
         pk["mlp_b1"] = f32(self.mlp[2].linear.bias).contiguous() if self.mlp[2].linear.bias is not None else None
         w1p, bsum, w1pl, w1inv, w2pl, w2inv, b2, wd, bd, dil = [], [], [], [], [], [], [], [], [], []
-        for blk in self.residual_layers:
+        for li, blk in enumerate(self.residual_layers):
             wc = f32(blk.conv_layer.conv.weight)                     # [2C, C, 3]
             wcond = f32(blk.conditioner_projection.conv.weight)[:, :, 0]   # [2C, E]
             w1 = torch.cat([wc[:, :, 0], wc[:, :, 1], wc[:, :, 2], wcond], dim=1)[perm].contiguous()  # [2C, 3C+E]
             w1p.append(w1)
             bsum.append((f32(blk.conv_layer.conv.bias) + f32(blk.conditioner_projection.conv.bias))[perm])
-            p1, i1 = pack(w1)
-            w1pl.append(p1); w1inv.append(i1)
-            p2, i2 = pack(f32(blk.output_projection.conv.weight)[:, :, 0])
-            w2pl.append(p2); w2inv.append(i2)
+            pl1, i1 = pack(w1, s1[li])
+            w1pl.append(pl1); w1inv.append(i1)
+            pl2, i2 = pack(f32(blk.output_projection.conv.weight)[:, :, 0], s2[li])
+            w2pl.append(pl2); w2inv.append(i2)
             b2.append(f32(blk.output_projection.conv.bias))
             wd.append(f32(blk.diffusion_projection.linear.weight))
             if blk.diffusion_projection.linear.bias is not None:
@@ -170,9 +183,9 @@ class WaveNet(nn.Module):
         pk["wd"] = torch.stack(wd).contiguous()
         pk["bd"] = torch.stack(bd).contiguous() if bd else None
         pk["dil"] = dil
-        pk["w_skip"], pk["w_skip_inv"] = pack(f32(self.skip_projection.conv.weight)[:, :, 0])
+        pk["w_skip"], pk["w_skip_inv"] = pack(f32(self.skip_projection.conv.weight)[:, :, 0], s_skip)
         pk["b_skip"] = f32(self.skip_projection.conv.bias).contiguous()
-        pk["w_out"], pk["w_out_inv"] = pack(f32(self.output_projection.conv.weight)[:, :, 0])
+        pk["w_out"], pk["w_out_inv"] = pack(f32(self.output_projection.conv.weight)[:, :, 0], s_out)
         pk["b_out"] = f32(self.output_projection.conv.bias).contiguous()
         self._pack, self._pack_key = pk, key
         return pk

@@ -2,16 +2,18 @@
 built from the same tap-GEMM kernels (reference: autograd through fish_diffusion/modules/wavenet.py:106-120,194-236
 inside GaussianDiffusion.p_losses, diffusion.py:129-151).
 
-Per residual block the backward is 6 GEMM-class launches (2x the forward FLOPs):
-  dz      = [dx_next/sqrt2 | d_skip] . W2            data gradient of the output projection  (K = 2C)
-  dW2     = [dx_next/sqrt2 | d_skip]^T . z           weight gradient (2 launches, K = time)
-  dW1     = dy^T . [x(t-d)+d, x(t)+d, x(t+d)+d, cond] weight gradient (4 launches: 3 taps + conditioner)
-  dx      = sum_tap dy(t -/+ d) . W1_tap + dx_next/sqrt2   data gradient of the dilated conv (K = 6C)
+Per residual block the backward is 5 GEMM launches (2x the forward FLOPs):
+  dz      = [dx_next/sqrt2 | d_skip] . W2                        data gradient of the output projection (K = 2C)
+  dW2     = [dx_next/sqrt2 ; d_skip]^T . z                       weight gradient (K = time)
+  dW1     = dy^T . [x(t-d)+d ; x(t)+d ; x(t+d)+d ; cond]         weight gradient of conv taps + conditioner, one GEMM
+  dx      = sum_tap dy(t -/+ d) . W1_tap + dx_next/sqrt2         data gradient of the dilated conv (K = 6C)
   dcond  += dy . Wc
 Weight gradients run on folded transposes [channels][B][Tp] (fd_fold_transpose) so that time is the contraction axis of
-the same K-major tensor-core kernel; the tap shift becomes a K offset of the second operand and the zero padding of the
-conv is the zero padding between items.  The tiny step-embedding MLP / diffusion projections stay under torch autograd
-(they act on [B or 1, C] vectors); their output d enters the block through the gate-bias tables.
+the same K-major tensor-core kernel; the tap shift is baked into the transpose (a TMA box must start on a 16-byte
+boundary) and the zero padding of the conv is the zero padding between items.  The operands of one weight-gradient
+GEMM are stacked row-wise so the result lands directly in the packed weight layout.  The tiny step-embedding MLP /
+diffusion projections stay under torch autograd (they act on [B or 1, C] vectors); their output d enters the block
+through the gate-bias tables and its gradient is a column sum of dx.
 """
 from __future__ import annotations
 
@@ -28,9 +30,32 @@ def _backend_for(pref, n_total, k_seg, num_seg):
     return N.BACKEND_SIMT
 
 
-def _pack(w2d, prec):
-    s = N.pow2_scale(w2d)
-    return N.pack_weight(w2d.contiguous(), prec, s), 1.0 / s
+def _bwd_packs(net, pk, device):
+    """Transposed packed weights of the data-gradient GEMMs for all layers, built with a few batched tensor ops per
+    optimisation step (cached next to the forward packs; power-of-two prescales reused from them: no host sync)."""
+    if pk.get("_bwd") is not None:
+        return pk["_bwd"]
+    prec = pk["prec"]
+    C, L = net.residual_channels, net.n_layers
+    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32)
+    W1 = pk["w1p_f32"]                                                   # [L, 2C, 3C+E] packed row order
+    W1T = W1[:, :, :3 * C].reshape(L, 2 * C, 3, C).permute(0, 3, 2, 1).reshape(L, C, 6 * C).contiguous()
+    WcT = W1[:, :, 3 * C:].transpose(1, 2).contiguous()                  # [L, E, 2C]
+    W2 = torch.stack([f32(b.output_projection.conv.weight)[:, :, 0] for b in net.residual_layers])   # [L, 2C, C]
+    W2T = W2.transpose(1, 2).contiguous()                                # [L, C, 2C]
+    W2T[:, :, :C] *= 1.0 / math.sqrt(2.0)                                # residual half carries the 1/sqrt2
+    bw = {"w1t": [], "w1t_inv": [], "wct": [], "wct_inv": [], "w2t": [], "w2t_inv": []}
+    for l in range(L):
+        s1, s2 = pk["s1"][l], pk["s2"][l]
+        bw["w1t"].append(N.pack_weight(W1T[l], prec, s1)); bw["w1t_inv"].append(1.0 / s1)
+        bw["wct"].append(N.pack_weight(WcT[l], prec, s1)); bw["wct_inv"].append(1.0 / s1)
+        bw["w2t"].append(N.pack_weight(W2T[l], prec, s2)); bw["w2t_inv"].append(1.0 / s2)
+    bw["wot"] = N.pack_weight(f32(net.output_projection.conv.weight)[:, :, 0].t().contiguous(), prec, pk["s_out"])
+    bw["wot_inv"] = 1.0 / pk["s_out"]
+    bw["wst"] = N.pack_weight(f32(net.skip_projection.conv.weight)[:, :, 0].t().contiguous(), prec, pk["s_skip"])
+    bw["wst_inv"] = 1.0 / pk["s_skip"]
+    pk["_bwd"] = bw
+    return bw
 
 
 class WaveNetTrainFn(torch.autograd.Function):
@@ -56,8 +81,8 @@ class WaveNetTrainFn(torch.autograd.Function):
         N.check(lib.fd_wavenet_gate_bias_from_d(N.ptr(d), N.ptr(pk["w1p_f32"]), N.ptr(pk["bias_sum"]), N.ptr(gb[0]),
                                                 N.ptr(gb[1]), N.ptr(gb[2]), L, Bs, C, 3 * C + E, st),
                 "fd_wavenet_gate_bias_from_d")
-        xs = [torch.empty((2, B, T, C), **i16) for _ in range(L + 1)]    # residual stream entering each layer
-        ys = [torch.empty((2, B, T, 2 * C), **i16) for _ in range(L)]    # gate/filter pre-activations (packed order)
+        xs = torch.empty((L + 1, 2, B, T, C), **i16)      # residual stream entering each layer (x_L is unused)
+        ys = torch.empty((L, 2, B, T, 2 * C), **i16)      # gate/filter pre-activations (packed order)
         z = torch.empty((2, B, T, C), **i16)
         skip_f32 = torch.empty((B, T, C), **f32)
         s_planes = torch.empty((2, B, T, C), **i16)
@@ -90,8 +115,9 @@ class WaveNetTrainFn(torch.autograd.Function):
         C, E, L = net.residual_channels, net.d_encoder, net.n_layers
         dev = d_eps.device
         pk = net._packed(dev)
+        bw = _bwd_packs(net, pk, dev)
         prec, pref = pk["prec"], pk["backend"]
-        perm, half, gate_tile = pk["perm"], pk["gate_tile"] // 2, pk["gate_tile"]
+        perm, gate_tile = pk["perm"], pk["gate_tile"]
         lib, st = N.lib(), N.stream_ptr(dev)
         i16 = dict(dtype=torch.int16, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -99,72 +125,75 @@ class WaveNetTrainFn(torch.autograd.Function):
         PAD = max(pk["dil"])
         Tp = (T + 2 * PAD + 63) // 64 * 64
         rows = B * T
+        KT = 3 * C + E
 
         # Gradient scaling: loss gradients are ~1/numel (1e-6 and below at training shapes), under the fp16 plane
         # range.  The whole backward chain therefore runs on S * gradient with S a power of two that puts
         # max|d_eps| into [32, 64); every quantity that leaves the chain (weight / bias / conditioner / step-vector
-        # gradients) is multiplied by 1/S exactly.  One host sync per backward to read max|d_eps|.
-        amax = float(d_eps.detach().abs().max())
-        S = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** math.floor(math.log2(64.0 / amax))
+        # gradients) is multiplied by 1/S exactly.  `net.grad_scale` (a float) skips the one host sync per backward.
+        if getattr(net, "grad_scale", None):
+            S = float(net.grad_scale)
+        else:
+            amax = float(d_eps.detach().abs().max())
+            S = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** math.floor(math.log2(64.0 / amax))
         inv_S = 1.0 / S
 
         # ---------------------------------------------------------------- helpers
-        def fold(planes, Cc, mode=0, scale=1.0, src_f32=None, aux=None, addvec=None, add_bstride=0, pad=None):
-            out = torch.empty((2, Cc, B, Tp), **i16)
+        def fold(planes, Cc, dst=None, row0=0, mode=0, scale=1.0, src_f32=None, aux=None, addvec=None, add_bstride=0,
+                 pad=None):
+            """planes [2,B,T,Cc] -> rows [row0, row0+Cc) of dst [2,R,B,Tp] (a fresh [2,Cc,B,Tp] when dst is None)"""
+            if dst is None:
+                dst = torch.empty((2, Cc, B, Tp), **i16)
             N.check(lib.fd_fold_transpose(N.ptr(planes), N.ptr(src_f32), N.ptr(aux), N.ptr(addvec), add_bstride,
-                                          N.ptr(out), B, T, Cc, Tp, PAD if pad is None else pad, scale, mode, gate_tile,
-                                          prec, st),
-                    "fd_fold_transpose")
-            return out
+                                          N.ptr(dst), B, T, Cc, Tp, PAD if pad is None else pad, scale, mode, gate_tile,
+                                          prec, dst.shape[1], row0, st), "fd_fold_transpose")
+            return dst
 
-        def wgrad(rowsT, R, colsT, Cc, shift=0):
-            """sum_{b,t} rows[b,t,r] * cols[b,t+shift,c]  -> fp32 [R, Cc]"""
+        def wgrad(rowsT, R, colsT, Cc):
+            """sum_{b,t} rows[b,t,r] * cols[b,t,c] / S  -> fp32 [R, Cc]  (per-item partials, then one reduction)"""
             part = torch.empty((B, R, Cc), **f32)
             N.gemm_cl(rowsT, Tp, colsT, Cc, B * Tp, B, R, [(0, 0, 0, Tp)], strides0=(B * Tp, Tp, R * B * Tp),
-                      w_kshift=shift, w_bstride_k=Tp, out_f32=part, prec=prec,
-                      backend=_backend_for(pref, Cc, Tp, 1))
+                      w_bstride_k=Tp, out_f32=part, prec=prec, backend=_backend_for(pref, Cc, Tp, 1))
             out = torch.empty((R, Cc), **f32)
             N.check(lib.fd_reduce_batch(N.ptr(part), N.ptr(out), B, R * Cc, inv_S, st), "fd_reduce_batch")
             return out
 
         def colsum(planes=None, f32t=None, Nn=0):
-            # gradients stored in planes are S-scaled (see below); fp32 inputs are not
+            # gradients stored in planes are S-scaled; fp32 inputs are not
             out = torch.zeros((B, Nn), **f32)
             N.check(lib.fd_colsum(N.ptr(planes), N.ptr(f32t), N.ptr(out), B, T, Nn, inv_S if planes is not None else 1.0,
                                   prec, st), "fd_colsum")
             return out
 
         def dgrad(src0, C0, w, w_inv, n_total, k_total, segs, **kw):
-            k_seg = segs[0][3]
             N.gemm_cl(src0, C0, w, n_total, k_total, B, T, segs, w_inv_scale=w_inv, prec=prec,
-                      backend=_backend_for(pref, n_total, k_seg, len(segs)), **kw)
+                      backend=_backend_for(pref, n_total, segs[0][3], len(segs)), **kw)
 
-        g = lambda name: getattr(net, name)
         grads = {}
 
         # ---------------------------------------------------------------- tail (wavenet.py:229-231)
         de = d_eps.detach().to(torch.float32).contiguous()
         de_planes = N.split_nwc(de, prec, scale=S)
-        deT = fold(de_planes, M)
-        hT = fold(sv["h_planes"], C)
-        grads["output_projection.w"] = wgrad(deT, M, hT, C)                       # [M, C]
+        grads["output_projection.w"] = wgrad(fold(de_planes, M), M, fold(sv["h_planes"], C), C)       # [M, C]
         grads["output_projection.b"] = colsum(f32t=de, Nn=M).sum(0)
-        WoT, WoT_inv = _pack(g("output_projection").conv.weight.detach()[:, :, 0].t().to(torch.float32), prec)
         dh_raw = torch.empty((B, T, C), **f32)
-        dgrad(de_planes, M, WoT, WoT_inv, C, M, [(0, 0, 0, M)], out_f32=dh_raw)
+        dgrad(de_planes, M, bw["wot"], bw["wot_inv"], C, M, [(0, 0, 0, M)], out_f32=dh_raw)
         dh_planes = torch.empty((2, B, T, C), **i16)
         N.check(lib.fd_relu_bwd(N.ptr(dh_raw), N.ptr(sv["h_planes"]), N.ptr(dh_planes), rows * C, 1.0, prec, st),
                 "fd_relu_bwd")
-        dhT = fold(dh_planes, C)
-        sT = fold(sv["s_planes"], C)
-        grads["skip_projection.w"] = wgrad(dhT, C, sT, C)
+        grads["skip_projection.w"] = wgrad(fold(dh_planes, C), C, fold(sv["s_planes"], C), C)
         grads["skip_projection.b"] = colsum(planes=dh_planes, Nn=C).sum(0)
-        WsT, WsT_inv = _pack(g("skip_projection").conv.weight.detach()[:, :, 0].t().to(torch.float32), prec)
         dskip_planes = torch.empty((2, B, T, C), **i16)                           # d(skip_l) = ds / sqrt(L), every layer
-        dgrad(dh_planes, C, WsT, WsT_inv, C, C, [(0, 0, 0, C)], out_planes=dskip_planes, planes_scale=inv_sqrtL)
-        dskipT = fold(dskip_planes, C)
+        dgrad(dh_planes, C, bw["wst"], bw["wst_inv"], C, C, [(0, 0, 0, C)], out_planes=dskip_planes,
+              planes_scale=inv_sqrtL)
         cs_skip = colsum(planes=dskip_planes, Nn=C)                              # [B, C]
-        condT = fold(sv["cond_planes"], E)
+        # stacked operands of the two weight-gradient GEMMs; the layer-invariant rows are written once
+        do_stack = torch.zeros((2, 2 * C, B, Tp), **i16)                         # [dx_next/sqrt2 ; d_skip]^T
+        fold(dskip_planes, C, dst=do_stack, row0=C)
+        xc_stack = torch.empty((2, KT, B, Tp), **i16)                            # [x(t-d)+d ; x(t)+d ; x(t+d)+d ; cond]^T
+        fold(sv["cond_planes"], E, dst=xc_stack, row0=3 * C)
+        dyT = torch.empty((2, 2 * C, B, Tp), **i16)
+        zT = torch.empty((2, C, B, Tp), **i16)
         d_cond = torch.zeros((B, T, E), **f32) if ctx.need_cond else None
 
         # ---------------------------------------------------------------- residual blocks, last to first
@@ -173,71 +202,64 @@ class WaveNetTrainFn(torch.autograd.Function):
         d_d = torch.zeros((Bs, L, C), **f32)
         dz = torch.empty((B, T, C), **f32)
         dx0 = torch.empty((B, T, C), **f32)       # fp32 copy of d(x_0), written by the layer-0 data gradient
+        dy = torch.empty((2, B, T, 2 * C), **i16)
+        dx_bufs = [torch.empty((2, B, T, C), **i16) for _ in range(2)]
+        gw1_all = torch.empty((L, 2 * C, KT), **f32)       # packed row order, un-permuted once at the end
+        gb1_all = torch.empty((L, 2 * C), **f32)
         for l in reversed(range(L)):
-            blk = net.residual_layers[l]
             dil = pk["dil"][l]
-            W2 = blk.output_projection.conv.weight.detach()[:, :, 0].to(torch.float32)          # [2C, C]
-            W2T = W2.t().clone()                                                                 # [C, 2C]
-            W2T[:, :C] *= inv_sqrt2                                                              # residual half: /sqrt2
-            W2Tp, W2T_inv = _pack(W2T, prec)
-            if dx_next is None:
-                N.gemm_cl(dskip_planes, C, W2Tp, C, 2 * C, B, T, [(0, 0, 0, C)], w_kshift=C, out_f32=dz,
-                          w_inv_scale=W2T_inv, prec=prec, backend=_backend_for(pref, C, C, 1))
+            if dx_next is None:     # K offset C selects the skip half of W2^T (aligned: C % 8 == 0)
+                N.gemm_cl(dskip_planes, C, bw["w2t"][l], C, 2 * C, B, T, [(0, 0, 0, C)], w_kshift=C, out_f32=dz,
+                          w_inv_scale=bw["w2t_inv"][l], prec=prec, backend=_backend_for(pref, C, C, 1))
             else:
-                N.gemm_cl(dx_next, C, W2Tp, C, 2 * C, B, T, [(0, 0, 0, C), (1, 0, 0, C)], src1=dskip_planes, C1=C,
-                          out_f32=dz, w_inv_scale=W2T_inv, prec=prec, backend=_backend_for(pref, C, C, 2))
-            dy = torch.empty((2, B, T, 2 * C), **i16)
+                N.gemm_cl(dx_next, C, bw["w2t"][l], C, 2 * C, B, T, [(0, 0, 0, C), (1, 0, 0, C)], src1=dskip_planes,
+                          C1=C, out_f32=dz, w_inv_scale=bw["w2t_inv"][l], prec=prec,
+                          backend=_backend_for(pref, C, C, 2))
             N.check(lib.fd_gate_bwd(N.ptr(dz), N.ptr(sv["ys"][l]), N.ptr(dy), rows, C, gate_tile, prec, st), "fd_gate_bwd")
-            # ---- weight gradients of the output projection: rows [residual | skip] x z
-            zT = fold(sv["ys"][l], C, mode=1)
-            gw2 = torch.empty((2 * C, C), **f32)
-            gb2 = torch.empty((2 * C,), **f32)
-            if dx_next is None:
-                gw2[:C].zero_(); gb2[:C].zero_()
-            else:
-                dxnT = fold(dx_next, C, scale=inv_sqrt2)
-                gw2[:C] = wgrad(dxnT, C, zT, C)
-                gb2[:C] = cs_next.sum(0) * inv_sqrt2
-            gw2[C:] = wgrad(dskipT, C, zT, C)
-            gb2[C:] = cs_skip.sum(0)
+            # ---- weight gradient of the output projection: rows [residual | skip] x z
+            fold(sv["ys"][l], C, dst=zT, mode=1)
+            if dx_next is not None:
+                fold(dx_next, C, dst=do_stack, row0=0, scale=inv_sqrt2)
+            gw2 = wgrad(do_stack, 2 * C, zT, C)
+            gb2 = torch.cat([cs_next.sum(0) * inv_sqrt2 if cs_next is not None else torch.zeros(C, **f32),
+                             cs_skip.sum(0)])
             grads[f"l{l}.w2"], grads[f"l{l}.b2"] = gw2, gb2
-            # ---- weight gradients of the dilated conv + conditioner projection (packed row order -> original)
-            dyT = fold(dy, 2 * C)
+            # ---- weight gradient of the dilated conv taps + conditioner projection in one GEMM (packed layout)
+            fold(dy, 2 * C, dst=dyT)
             addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
-            gw1 = torch.empty((2 * C, C, 3), **f32)
             for j, sh in enumerate((-dil, 0, dil)):
-                # the tap shift is baked into the folded transpose (data starts at column PAD - shift): a TMA box must
-                # start on a 16-byte boundary, so an element-granular K offset on the operand is not an option
-                xdT = fold(sv["xs"][l], C, addvec=addvec, add_bstride=C if Bs > 1 else 0, pad=PAD - sh)
-                gw1[perm, :, j] = wgrad(dyT, 2 * C, xdT, C)
-            gwc = torch.empty((2 * C, E), **f32)
-            gwc[perm] = wgrad(dyT, 2 * C, condT, E)
-            gb1 = torch.empty((2 * C,), **f32)
-            gb1[perm] = colsum(planes=dy, Nn=2 * C).sum(0)
-            grads[f"l{l}.w1"], grads[f"l{l}.wc"], grads[f"l{l}.b1"] = gw1, gwc, gb1
+                fold(sv["xs"][l], C, dst=xc_stack, row0=j * C, addvec=addvec, add_bstride=C if Bs > 1 else 0,
+                     pad=PAD - sh)
+            gw1_all[l] = wgrad(dyT, 2 * C, xc_stack, KT)
+            gb1_all[l] = colsum(planes=dy, Nn=2 * C).sum(0)
             # ---- data gradients: dx_l = conv^T(dy) + dx_next/sqrt2 ;  dcond += dy . Wc
-            Wc = blk.conv_layer.conv.weight.detach().to(torch.float32)                # [2C, C, 3]
-            W1T = torch.cat([Wc[perm, :, j].t() for j in range(3)], dim=1)            # [C, 3*2C], packed dy order
-            W1Tp, W1T_inv = _pack(W1T, prec)
-            dx_l = torch.empty((2, B, T, C), **i16)
-            dgrad(dy, 2 * C, W1Tp, W1T_inv, C, 6 * C, [(0, dil, 0, 2 * C), (0, 0, 0, 2 * C), (0, -dil, 0, 2 * C)],
-                  res_planes=dx_next, res_scale=inv_sqrt2, out_planes=dx_l, out_f32=dx0 if l == 0 else None)
+            dx_l = dx_bufs[l & 1]
+            dgrad(dy, 2 * C, bw["w1t"][l], bw["w1t_inv"][l], C, 6 * C,
+                  [(0, dil, 0, 2 * C), (0, 0, 0, 2 * C), (0, -dil, 0, 2 * C)], res_planes=dx_next, res_scale=inv_sqrt2,
+                  out_planes=dx_l, out_f32=dx0 if l == 0 else None)
             if d_cond is not None:
-                WcT, WcT_inv = _pack(blk.conditioner_projection.conv.weight.detach()[perm, :, 0].t().to(torch.float32),
-                                     prec)
-                dgrad(dy, 2 * C, WcT, WcT_inv * inv_S, E, 2 * C, [(0, 0, 0, 2 * C)], out_f32=d_cond, out_accum=True)
+                dgrad(dy, 2 * C, bw["wct"][l], bw["wct_inv"][l] * inv_S, E, 2 * C, [(0, 0, 0, 2 * C)], out_f32=d_cond,
+                      out_accum=True)
             cs_l = colsum(planes=dx_l, Nn=C)
             dd = cs_l if cs_next is None else cs_l - cs_next * inv_sqrt2               # d wrt the step vector d_l
             d_d[:, l, :] = dd if Bs > 1 else dd.sum(0, keepdim=True)
             dx_next, cs_next = dx_l, cs_l
 
+        # packed -> reference layouts for all layers at once
+        gw1_o = torch.empty_like(gw1_all)
+        gw1_o[:, perm] = gw1_all
+        gb1_o = torch.empty_like(gb1_all)
+        gb1_o[:, perm] = gb1_all
+        for l in range(L):
+            grads[f"l{l}.w1"] = gw1_o[l, :, :3 * C].reshape(2 * C, 3, C).permute(0, 2, 1)
+            grads[f"l{l}.wc"] = gw1_o[l, :, 3 * C:]
+            grads[f"l{l}.b1"] = gb1_o[l]
+
         # ---------------------------------------------------------------- head (wavenet.py:211-212)
         # dx_next now is d(x_0) where x_0 = relu(input_projection(x)): mask with x_0 > 0
         dx0m = torch.empty((2, B, T, C), **i16)
         N.check(lib.fd_relu_bwd(N.ptr(dx0), N.ptr(sv["xs"][0]), N.ptr(dx0m), rows * C, 1.0, prec, st), "fd_relu_bwd")
-        dx0mT = fold(dx0m, C)
-        xnT = fold(sv["x_planes"], M)
-        grads["input_projection.w"] = wgrad(dx0mT, C, xnT, M)
+        grads["input_projection.w"] = wgrad(fold(dx0m, C), C, fold(sv["x_planes"], M), M)
         grads["input_projection.b"] = colsum(planes=dx0m, Nn=C).sum(0)
 
         out = [None, None, d_cond, d_d]

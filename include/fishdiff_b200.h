@@ -209,10 +209,12 @@ int fd_wavenet_gate_bias_from_d(const float* d, const float* w1p, const float* b
                                 float* gb_hi, int L, int Bs, int C, int KT, void* stream);
 /* planes [2][B][T][C] -> planes [2][C][B][Tp] (item b at columns [pad, pad+T) of its Tp span, zeros elsewhere).
  * mode 0: value*scale (+ addvec[b*add_bstride + c]); mode 1: src is a packed pre-activation tensor with 2C columns,
- * value = sigmoid(g)*tanh(f); mode 2: value = src_f32 * (aux_planes > 0) (ReLU backward). */
+ * value = sigmoid(g)*tanh(f); mode 2: value = src_f32 * (aux_planes > 0) (ReLU backward).
+ * The C rows may be written at row offset dst_row0 of a taller destination with dst_rows rows (stacked operands of the
+ * weight-gradient GEMMs); dst_rows <= 0 means dst_rows = C, dst_row0 = 0. */
 int fd_fold_transpose(const uint16_t* src_planes, const float* src_f32, const uint16_t* aux_planes, const float* addvec,
                       int add_bstride, uint16_t* dst, int B, int T, int C, int Tp, int pad, float scale, int mode,
-                      int gate_tile, int prec, void* stream);
+                      int gate_tile, int prec, int dst_rows, int dst_row0, void* stream);
 /* backward of z = sigmoid(g)*tanh(f) (wavenet.py:114-115): dz fp32 [rows][C], y planes [2][rows][2C] -> dy planes */
 int fd_gate_bwd(const float* dz, const uint16_t* y_planes, uint16_t* dy_planes, long long rows, int C, int gate_tile,
                 int prec, void* stream);

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check-ddp", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced network (tests)")
+    ap.add_argument("--fp16-hook", action="store_true", help="use the reference's fp16_compress_hook")
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -79,7 +80,7 @@ def main():
         sys.exit(0 if worst < 1e-4 else 1)
 
     diff = build(dev, cfg)
-    tr = DenoiserTrainer(diff, device=dev)
+    tr = DenoiserTrainer(diff, device=dev, fp16_compress=args.fp16_hook)
     for _ in range(args.warmup):
         tr.step(feats, mel)
     torch.cuda.synchronize()
@@ -111,7 +112,7 @@ def main():
             "fwd_only_ms": fwd_ms, "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
             "gpu_launches_per_step": (N.launch_count() - l0) // (2 * args.steps) if False else None,
             "loss": float(loss), "optimizer": "AdamW(8e-4, wd 1e-2, betas (0.9,0.98), eps 1e-9), clip 0.5",
-            "ddp": "torch DDP over NCCL, fp16_compress_hook, static_graph" if world > 1 else "single process",
+            "ddp": ("torch DDP over NCCL, static_graph" + (", fp16_compress_hook" if args.fp16_hook else "")) if world > 1 else "single process",
             "dtype": "f32 (3x fp16 split-product tcgen05)", "data": "synthetic"}))
     if world > 1:
         torch.distributed.destroy_process_group()
