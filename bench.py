@@ -288,9 +288,43 @@ def main():
             voc = {"config": "config_v1.json (hop 512)", "B": B, "T": T, "ms": v_ms,
                    "rtf_agg": world * B * audio_s / (v_ms * 1e-3), "rtf_stream": audio_s / (v_ms * 1e-3),
                    "tflops": world * B * T * 652.1e6 / (v_ms * 1e-3) / 1e12}
+            # ---- config #5 flavour: sampler + vocoder back to back on one batch (B=16, T=4000), audio-seconds/s
+            Bs5 = min(16, B)
+            f5 = feats[:Bs5].contiguous()
+            f0_5 = f0[:Bs5].contiguous()
+
+            def synth_step():
+                m5 = diff(f5, sampler_interval=interval, noise_predictor="naive")          # [B,T,M] ln-mel
+                m5 = m5.transpose(1, 2).contiguous()
+                return gen(m5, f0_5, seed=1)
+
+            synth_step()
+            barrier()
+            ev0.record()
+            synth_step()
+            ev1.record()
+            barrier()
+            s_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
+            voc["synth_e2e"] = {"B": Bs5, "T": T, "ms": s_ms, "audio_seconds_per_sec": world * Bs5 * audio_s / (s_ms * 1e-3),
+                                "what": "100-eval DDPM sampler + NSF-HiFiGAN (hop 512) per batch, device resident"}
             del gen, mel
         except Exception as ex:  # noqa: BLE001
             voc = {"error": repr(ex)[:300]}
+
+    # ---- the reference's DEFAULT predictor for interval != 1 is UniPC: same 100 denoiser evaluations
+    unipc = None
+    if not args.no_vocoder:
+        try:
+            diff(feats, sampler_interval=interval, noise_predictor="unipc")
+            barrier()
+            ev0.record()
+            diff(feats, sampler_interval=interval, noise_predictor="unipc")
+            ev1.record()
+            barrier()
+            u_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
+            unipc = {"ms_per_step": u_ms, "mel_frames_per_sec": world * B * T / (u_ms * 1e-3)}
+        except Exception as ex:  # noqa: BLE001
+            unipc = {"error": repr(ex)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -311,7 +345,7 @@ def main():
                        "backend": backend_name, "precision": args.precision,
                        "l2": "inputs (features 131 MB + weights 420 MB + 1 GB activations per layer) larger than L2"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "vocoder": voc, "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
+            "vocoder": voc, "unipc": unipc, "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
         }
         print(json.dumps(line))
     if world > 1:

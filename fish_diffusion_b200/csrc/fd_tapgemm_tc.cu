@@ -213,7 +213,10 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+        const int m_tile = tile / num_n_tiles;
+        // rotate the column tile with the row tile: with a grid that is a multiple of num_n_tiles every CTA would
+        // otherwise see the same n-tile forever, and epilogue costs differ per n-tile (residual vs skip columns)
+        const int n_tile = (tile % num_n_tiles + m_tile) % num_n_tiles;
         const int b = m_tile / tiles_t, t0 = (m_tile % tiles_t) * BLOCK_M;
         const int n0 = n_tile * BLOCK_N;
         int koff = 0;
@@ -282,7 +285,10 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
     constexpr int HALVES = BLOCK_N >= 64 ? 2 : 1;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+      const int m_tile = tile / num_n_tiles;
+        // rotate the column tile with the row tile: with a grid that is a multiple of num_n_tiles every CTA would
+        // otherwise see the same n-tile forever, and epilogue costs differ per n-tile (residual vs skip columns)
+        const int n_tile = (tile % num_n_tiles + m_tile) % num_n_tiles;
       const int b = m_tile / tiles_t, t0 = (m_tile % tiles_t) * BLOCK_M;
       const int n0 = n_tile * BLOCK_N;
       const int t = t0 + row;

@@ -202,11 +202,15 @@ class GaussianDiffusion(nn.Module):
     def denorm_spec(self, x):
         return self._affine(x, inverse=True)
 
+    def _rng_seed(self):
+        s = getattr(self, "_seed_override", None)
+        return (int(s) if s is not None else int(torch.initial_seed())) & (2 ** 63 - 1)
+
     def _randn(self, shape, device):
         out = torch.empty(shape, dtype=torch.float32, device=device)
         self._philox_calls += 1
-        N.check(N.lib().fd_randn(N.ptr(out), out.numel(), int(torch.initial_seed()) & (2 ** 63 - 1),
-                                 self._philox_calls << 20, N.stream_ptr(device)), "fd_randn")
+        N.check(N.lib().fd_randn(N.ptr(out), out.numel(), self._rng_seed(), self._philox_calls << 20,
+                                 N.stream_ptr(device)), "fd_randn")
         return out
 
     @staticmethod
@@ -280,10 +284,18 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def forward(self, features, sampler_interval=None, progress: bool = False, skip_steps: int = 0,
                 original_mel: torch.Tensor = None, noise_predictor: str = None, x_masks: torch.Tensor = None,
-                cond_masks: torch.Tensor = None, x_T: torch.Tensor = None, step_noises=None):
+                cond_masks: torch.Tensor = None, x_T: torch.Tensor = None, step_noises=None, seed: int = None):
         """Reference contract (diffusion.py:196-313): features [B,T,E] -> mel [B,T,M].
         Extra (parity tests): x_T [B,M,T] replaces the initial randn / the q_sample noise of shallow diffusion,
         step_noises[i] [B,M,T] replaces the i-th randn_like of the naive predictor."""
+        if seed is not None:
+            # reproducible call: Philox streams are (seed, draw index within this call) instead of the running counter
+            self._seed_override, self._philox_calls = int(seed), 0
+            try:
+                return self.forward(features, sampler_interval, progress, skip_steps, original_mel, noise_predictor,
+                                    x_masks, cond_masks, x_T, step_noises, None)
+            finally:
+                self._seed_override = None
         if sampler_interval is None:
             sampler_interval = self.sampler_interval
         if noise_predictor is None:
@@ -318,7 +330,7 @@ class GaussianDiffusion(nn.Module):
             from tqdm import tqdm
             it = tqdm(chunks)
         eps = torch.empty((B, T, M), dtype=torch.float32, device=dev)
-        seed = int(torch.initial_seed()) & (2 ** 63 - 1)
+        seed = self._rng_seed()
 
         def denoise(xp, t_float, masks=True, out=eps):
             steps = torch.tensor([t_float], dtype=torch.float32, device=dev)

@@ -1,0 +1,67 @@
+"""CPU tests of the 'next' rows N1-N3: batching plan, DiffSinger feature fusion, Lightning-checkpoint key handling."""
+import numpy as np
+import pytest
+import torch
+
+from fish_diffusion_b200 import DiffSinger, load_checkpoint, pitch_to_scale, plan_batches
+from fish_diffusion_b200.pipeline import padding_waste
+
+MODEL_CFG = dict(
+    text_encoder=dict(type="NaiveProjectionEncoder", input_size=24, output_size=32),
+    speaker_encoder=dict(type="NaiveProjectionEncoder", input_size=10, output_size=32, use_embedding=True),
+    pitch_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=32, preprocessing=pitch_to_scale),
+    diffusion=dict(type="GaussianDiffusion", mel_channels=16, sampler_interval=10, spec_min=[-5.0], spec_max=[0.0],
+                   denoiser=dict(type="WaveNetDenoiser", mel_channels=16, d_encoder=32, residual_channels=64,
+                                 residual_layers=2, use_linear_bias=True)),
+)
+
+
+def test_plan_batches_covers_everything_once():
+    rng = np.random.RandomState(0)
+    lengths = rng.randint(1, 4000, size=137).tolist()
+    batches = plan_batches(lengths, max_batch=32, bucket=128, max_frames=32 * 4096)
+    seen = sorted(i for idx, _ in batches for i in idx)
+    assert seen == list(range(137))
+    for idx, T in batches:
+        assert 1 <= len(idx) <= 32 and T % 128 == 0
+        assert all(lengths[i] <= T for i in idx) and max(lengths[i] for i in idx) > T - 128
+        assert len(idx) * T <= 32 * 4096 or len(idx) == 1
+    assert padding_waste(lengths, batches) < 0.12          # length-sorted buckets keep the padding small
+    with pytest.raises(ValueError):
+        plan_batches([5, 0])
+
+
+def test_diffsinger_forward_features_matches_definition():
+    torch.manual_seed(0)
+    m = DiffSinger(MODEL_CFG)
+    B, T = 3, 11
+    contents = torch.randn(B, T, 24)
+    speakers = torch.tensor([1, 4, 9])
+    pitches = torch.rand(B, T) * 900 + 60
+    lens = torch.tensor([11, 7, 3])
+    out = m.forward_features(speakers=speakers, contents=contents, contents_lens=lens, contents_max_len=T, mel_lens=lens,
+                             mel_max_len=T, pitches=pitches)
+    te, se, pe = m.text_encoder.projection, m.speaker_encoder.embedding, m.pitch_encoder.projection
+    scale = ((pitches - 50.0) / 1050.0).clamp(0, 1)[..., None]
+    want = contents @ te.weight.T + te.bias + se.weight[speakers][:, None] + scale @ pe.weight.T + pe.bias
+    assert torch.allclose(out["features"], want, atol=1e-6)
+    assert out["features"].shape == (B, T, 32)
+    assert torch.equal(out["x_masks"], torch.arange(T)[None] >= lens[:, None])
+    assert out["cond_masks"] is out["x_masks"]
+    # reference parameter names (model.* keys of a Lightning checkpoint)
+    keys = set(m.state_dict())
+    assert {"text_encoder.projection.weight", "speaker_encoder.embedding.weight", "pitch_encoder.projection.bias",
+            "diffusion.denoise_fn.input_projection.conv.weight", "diffusion.naive_noise_predictor.clip_min",
+            "diffusion.spec_min"} <= keys
+
+
+def test_load_checkpoint_prefix_and_vocoder_keys(tmp_path):
+    torch.manual_seed(1)
+    src, dst = DiffSinger(MODEL_CFG), DiffSinger(MODEL_CFG)
+    sd = {"model." + k: v for k, v in src.state_dict().items()}
+    sd["vocoder.model.conv_pre.weight"] = torch.zeros(3)          # dropped like utils/inference.py:18-22
+    torch.save({"state_dict": sd}, tmp_path / "a.ckpt")
+    missing, unexpected = load_checkpoint(dst, str(tmp_path / "a.ckpt"), device="cpu")
+    assert not missing and not unexpected
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
