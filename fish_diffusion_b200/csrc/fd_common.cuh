@@ -231,10 +231,11 @@ __device__ __forceinline__ void fd_store_f32(float* p, const float (&y)[V]) {
 // Epilogues.  Each handles V consecutive output columns [n0, n0+V) of row (b,t) with raw
 // accumulators acc[].  `bias*` pointers may be shared-memory or global (generic loads).
 // ------------------------------------------------------------------------------------------------
-template <int V>
+template <int V, int PREC = -1>
 __device__ __forceinline__ void fd_epi_linear(const FdTapGemm& p, int b, int t, int n0,
                                               const float (&acc)[V], const float* bias_tile /*[n - tile_n0] or null*/,
                                               int tile_n0) {
+  const int prec = PREC < 0 ? p.prec : PREC;   // compile-time in the tensor-core kernel
   const size_t row = (size_t)b * p.T + t;
   const size_t off = row * p.n_total + n0;
   const size_t plane_elems = (size_t)p.B * p.T * p.n_total;
@@ -257,7 +258,7 @@ __device__ __forceinline__ void fd_epi_linear(const FdTapGemm& p, int b, int t, 
     for (int i = 0; i < V; ++i) y[i] += a[i];
   }
   if (p.res_planes != nullptr) {
-    float a[V]; fd_load_planes<V>(p.res_planes, plane_elems, off, a, p.prec);
+    float a[V]; fd_load_planes<V>(p.res_planes, plane_elems, off, a, prec);
 #pragma unroll
     for (int i = 0; i < V; ++i) y[i] += a[i] * p.res_scale;
   }
@@ -283,18 +284,19 @@ __device__ __forceinline__ void fd_epi_linear(const FdTapGemm& p, int b, int t, 
       else if (p.act == FD_ACT_LRELU) v = v > 0.f ? v : v * p.act_slope;
       y[i] = masked ? 0.f : v;
     }
-    fd_store_planes<V>(p.out_planes, plane_elems, off, y, p.prec);
+    fd_store_planes<V>(p.out_planes, plane_elems, off, y, prec);
   }
 }
 
 // gate epilogue: V gate accumulators + V filter accumulators for residual channels [zc0, zc0+V);
 // gb_* point at the bias of the FIRST gate column of this thread's chunk, gf_* at the first filter col.
-template <int V>
+template <int V, int PREC = -1>
 __device__ __forceinline__ void fd_epi_gate(const FdTapGemm& p, int b, int t, int zc0,
                                             const float (&g)[V], const float (&f)[V],
                                             const float* full_g, const float* full_f,
                                             const float* lo_g, const float* lo_f,
                                             const float* hi_g, const float* hi_f) {
+  const int prec = PREC < 0 ? p.prec : PREC;   // compile-time in the tensor-core kernel
   float z[V], yg8[V], yf8[V];
   const bool e_lo = t < p.dil, e_hi = t + p.dil >= p.T;
 #pragma unroll
@@ -311,17 +313,18 @@ __device__ __forceinline__ void fd_epi_gate(const FdTapGemm& p, int b, int t, in
     const int ng = (zc0 / half) * p.gate_tile + (zc0 % half);
     const size_t yplane = (size_t)p.B * p.T * p.n_total;
     const size_t yoff = ((size_t)b * p.T + t) * p.n_total;
-    fd_store_planes<V>(p.y_planes, yplane, yoff + ng, yg8, p.prec);
-    fd_store_planes<V>(p.y_planes, yplane, yoff + ng + half, yf8, p.prec);
+    fd_store_planes<V>(p.y_planes, yplane, yoff + ng, yg8, prec);
+    fd_store_planes<V>(p.y_planes, yplane, yoff + ng + half, yf8, prec);
   }
   const size_t plane_elems = (size_t)p.B * p.T * p.C;
   const size_t off = ((size_t)b * p.T + t) * p.C + zc0;
-  fd_store_planes<V>(p.out_planes, plane_elems, off, z, p.prec);
+  fd_store_planes<V>(p.out_planes, plane_elems, off, z, prec);
 }
 
-template <int V>
+template <int V, int PREC = -1>
 __device__ __forceinline__ void fd_epi_mag(const FdTapGemm& p, int b, int t, int zc0,
                                            const float (&re)[V], const float (&im)[V]) {
+  const int prec = PREC < 0 ? p.prec : PREC;   // compile-time in the tensor-core kernel
   float z[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -330,13 +333,14 @@ __device__ __forceinline__ void fd_epi_mag(const FdTapGemm& p, int b, int t, int
   }
   const size_t plane_elems = (size_t)p.B * p.T * p.C;
   const size_t off = ((size_t)b * p.T + t) * p.C + zc0;
-  fd_store_planes<V>(p.out_planes, plane_elems, off, z, p.prec);
+  fd_store_planes<V>(p.out_planes, plane_elems, off, z, prec);
 }
 
 // residual/skip epilogue for V consecutive packed columns [n0, n0+V) (n0 < C: residual, else skip)
-template <int V>
+template <int V, int PREC = -1>
 __device__ __forceinline__ void fd_epi_res_skip(const FdTapGemm& p, int b, int t, int n0,
                                                 const float (&acc)[V], const float* bias /*indexed by i*/) {
+  const int prec = PREC < 0 ? p.prec : PREC;   // compile-time in the tensor-core kernel
   const size_t row = (size_t)b * p.T + t;
   const size_t plane_elems = (size_t)p.B * p.T * p.C;
   float y[V];
@@ -346,10 +350,10 @@ __device__ __forceinline__ void fd_epi_res_skip(const FdTapGemm& p, int b, int t
     if (p.last_layer) return;  // the residual stream is not consumed after the last layer
     const size_t off = row * p.C + n0;
     float x[V];
-    fd_load_planes<V>(p.x_planes, plane_elems, off, x, p.prec);
+    fd_load_planes<V>(p.x_planes, plane_elems, off, x, prec);
 #pragma unroll
     for (int i = 0; i < V; ++i) x[i] = (x[i] + y[i]) * 0.70710678118654752440f;
-    fd_store_planes<V>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane_elems, off, x, p.prec);
+    fd_store_planes<V>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane_elems, off, x, prec);
   } else {
     const size_t off = row * p.C + (n0 - p.C);
     if (!p.first_layer) {
@@ -360,7 +364,7 @@ __device__ __forceinline__ void fd_epi_res_skip(const FdTapGemm& p, int b, int t
     if (p.last_layer) {
 #pragma unroll
       for (int i = 0; i < V; ++i) y[i] *= p.skip_scale;
-      fd_store_planes<V>(p.skip_planes, plane_elems, off, y, p.prec);
+      fd_store_planes<V>(p.skip_planes, plane_elems, off, y, prec);
     } else {
       fd_store_f32<V>(p.skip_f32 + off, y);
     }

@@ -112,17 +112,26 @@ __device__ __forceinline__ void tmem_wait16(float (&v)[16]) {
 // Warp-private 32x32 fp32 transpose through shared memory (16-byte chunks XOR-swizzled by row & 7, conflict-free
 // on both sides).  In: lane l owns row l (v[0..31]).  Out: a[p] = row (4p + l/8), columns 4*(l%8)..+3, i.e. eight
 // lanes cover one 128-byte row segment -> fully coalesced global accesses in the epilogue.
-__device__ __forceinline__ void warp_transpose_32x32(float* scratch, int lane, const float (&v)[32], float4 (&a)[8]) {
-  float4* s4 = reinterpret_cast<float4*>(scratch);
+// (explicit shared-space ld/st: the scratch pointer is derived by integer alignment arithmetic, which makes the
+// compiler fall back to generic LD/ST with their longer latency)
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void warp_transpose_32x32(uint32_t scratch, int lane, const float (&v)[32], float4 (&a)[8]) {
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    s4[lane * 8 + (k ^ (lane & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    sts128(scratch + 16u * (lane * 8 + (k ^ (lane & 7))), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
   const int j = lane & 7, rsub = lane >> 3;
 #pragma unroll
   for (int pp = 0; pp < 8; ++pp) {
     const int r = pp * 4 + rsub;
-    a[pp] = s4[r * 8 + (j ^ (r & 7))];
+    a[pp] = lds128(scratch + 16u * (r * 8 + (j ^ (r & 7))));
   }
   __syncwarp();
 }
@@ -163,7 +172,7 @@ struct Cfg {
                                     (2 * NUM_STAGES + 2 * ACC_STAGES) * 8 + 16 + SCRATCH_BYTES;
 };
 
-template <int BLOCK_N, int BLOCK_K, int EPI>
+template <int BLOCK_N, int BLOCK_K, int EPI, int PREC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                      const __grid_constant__ CUtensorMap tm_w, const FdTapGemm p) {
@@ -241,7 +250,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
   } else if (warp == 1) {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t fmt = p.prec == FD_F16 ? 0u : 1u;
+      const uint32_t fmt = PREC == FD_F16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                              ((uint32_t)(BLOCK_M >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
@@ -334,9 +343,9 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
               for (int i = 0; i < 8; ++i) { g8[i] = g[h * 8 + i]; f8[i] = f[h * 8 + i]; }
               const int cc = c0 + h * 8;
               if (EPI == FD_EPI_MAG)
-                fd_epi_mag<8>(p, b, t, n_tile * HALF + cc, g8, f8);
+                fd_epi_mag<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8);
               else
-                fd_epi_gate<8>(p, b, t, n_tile * HALF + cc, g8, f8, bias_s + cc, bias_s + HALF + cc,
+                fd_epi_gate<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8, bias_s + cc, bias_s + HALF + cc,
                                bias_s + BLOCK_N + cc, bias_s + BLOCK_N + HALF + cc, bias_s + 2 * BLOCK_N + cc,
                                bias_s + 2 * BLOCK_N + HALF + cc);
             }
@@ -347,7 +356,8 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
         //      smem scratch so that 8 lanes cover one 128-byte row segment; all global loads of a half-chunk are issued
         //      before the TMEM wait (latency overlap); per-item math is the shared V=4 epilogue of fd_common.cuh order.
         constexpr int PER = BLOCK_N / HALVES;
-        float* my_scratch = scratch_s + (warp - EPI_WARP0) * 1024;
+        const uint32_t my_scratch = smem_u32(scratch_s) + (warp - EPI_WARP0) * 4096;
+        const uint32_t bias_addr = smem_u32(bias_s);
         const int j4 = (lane & 7) * 4, rsub = lane >> 3;
         const int rbase = t0 + q * 32 + rsub;            // time index of pass 0
         for (int c = 0; c < PER; c += 32) {
@@ -356,7 +366,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
           float v[32];
           tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
           tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
-          const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + col);
+          const float4 bias4 = lds128(bias_addr + 4u * col);
           if (EPI == FD_EPI_RES_SKIP) {
             const bool is_res = n0 < p.C;
             const size_t plane = (size_t)p.B * p.T * p.C;
@@ -392,13 +402,13 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 if (p.last_layer) continue;
                 const uint4 o = op[pp];
                 float x4[4];
-                x4[0] = fd_combine((uint16_t)(o.x & 0xffff), (uint16_t)(o.z & 0xffff), p.prec);
-                x4[1] = fd_combine((uint16_t)(o.x >> 16), (uint16_t)(o.z >> 16), p.prec);
-                x4[2] = fd_combine((uint16_t)(o.y & 0xffff), (uint16_t)(o.w & 0xffff), p.prec);
-                x4[3] = fd_combine((uint16_t)(o.y >> 16), (uint16_t)(o.w >> 16), p.prec);
+                x4[0] = fd_combine((uint16_t)(o.x & 0xffff), (uint16_t)(o.z & 0xffff), PREC);
+                x4[1] = fd_combine((uint16_t)(o.x >> 16), (uint16_t)(o.z >> 16), PREC);
+                x4[2] = fd_combine((uint16_t)(o.y & 0xffff), (uint16_t)(o.w & 0xffff), PREC);
+                x4[3] = fd_combine((uint16_t)(o.y >> 16), (uint16_t)(o.w >> 16), PREC);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) x4[i] = (x4[i] + y[i]) * 0.70710678118654752440f;
-                fd_store_planes<4>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane, ro + n, x4, p.prec);
+                fd_store_planes<4>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane, ro + n, x4, PREC);
               } else {
                 if (!p.first_layer) {
                   const uint4 o = op[pp];
@@ -408,7 +418,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 if (p.last_layer) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) y[i] *= p.skip_scale;
-                  fd_store_planes<4>(p.skip_planes, plane, ro + (n - p.C), y, p.prec);
+                  fd_store_planes<4>(p.skip_planes, plane, ro + (n - p.C), y, PREC);
                 } else {
                   *reinterpret_cast<float4*>(p.skip_f32 + ro + (n - p.C)) = make_float4(y[0], y[1], y[2], y[3]);
                 }
@@ -454,10 +464,10 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 if (p.addend != nullptr) { y[0] += ad[k].x; y[1] += ad[k].y; y[2] += ad[k].z; y[3] += ad[k].w; }
                 if (p.res_f32 != nullptr) { y[0] += rs[k].x; y[1] += rs[k].y; y[2] += rs[k].z; y[3] += rs[k].w; }
                 if (p.res_planes != nullptr) {
-                  y[0] += p.res_scale * fd_combine((uint16_t)(rh[k].x & 0xffff), (uint16_t)(rl[k].x & 0xffff), p.prec);
-                  y[1] += p.res_scale * fd_combine((uint16_t)(rh[k].x >> 16), (uint16_t)(rl[k].x >> 16), p.prec);
-                  y[2] += p.res_scale * fd_combine((uint16_t)(rh[k].y & 0xffff), (uint16_t)(rl[k].y & 0xffff), p.prec);
-                  y[3] += p.res_scale * fd_combine((uint16_t)(rh[k].y >> 16), (uint16_t)(rl[k].y >> 16), p.prec);
+                  y[0] += p.res_scale * fd_combine((uint16_t)(rh[k].x & 0xffff), (uint16_t)(rl[k].x & 0xffff), PREC);
+                  y[1] += p.res_scale * fd_combine((uint16_t)(rh[k].x >> 16), (uint16_t)(rl[k].x >> 16), PREC);
+                  y[2] += p.res_scale * fd_combine((uint16_t)(rh[k].y & 0xffff), (uint16_t)(rl[k].y & 0xffff), PREC);
+                  y[3] += p.res_scale * fd_combine((uint16_t)(rh[k].y >> 16), (uint16_t)(rl[k].y >> 16), PREC);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) y[i] *= p.post_scale;
@@ -475,7 +485,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                     else if (p.act == FD_ACT_LRELU) w = w > 0.f ? w : w * p.act_slope;
                     o4[i] = mk[k] ? 0.f : w;
                   }
-                  fd_store_planes<4>(p.out_planes, plane, off, o4, p.prec);
+                  fd_store_planes<4>(p.out_planes, plane, off, o4, PREC);
                 }
               }
             }
@@ -497,8 +507,8 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v8[i] = v[h * 8 + i];
                 const int cc = col + h * 8;
-                if (EPI == FD_EPI_LINEAR) fd_epi_linear<8>(p, b, t, n0 + cc, v8, bias_s, n0);
-                else fd_epi_res_skip<8>(p, b, t, n0 + cc, v8, bias_s + cc);
+                if (EPI == FD_EPI_LINEAR) fd_epi_linear<8, PREC>(p, b, t, n0 + cc, v8, bias_s, n0);
+                else fd_epi_res_skip<8, PREC>(p, b, t, n0 + cc, v8, bias_s + cc);
               }
             }
           }
@@ -593,11 +603,12 @@ int launch_cfg(const FdTapGemm& p, cudaStream_t stream) {
   rc = make_w_map(&tmw, p.w, p.n_total, p.k_total, BLOCK_N, BLOCK_K);
   if (rc) return rc;
 
-  auto kern = fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto kern = p.prec == FD_F16 ? fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI, FD_F16>
+                               : fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI, FD_BF16>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[p.prec == FD_F16 ? 0 : 1]) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set[p.prec == FD_F16 ? 0 : 1] = true;
   }
   if (g_num_sms == 0) {
     int dev = 0;
