@@ -151,20 +151,30 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
 template <int BLOCK_N, int BLOCK_K, int EPI>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int W_BYTES_RAW = BLOCK_N * BLOCK_K * 2;
-  static constexpr int W_BYTES = (W_BYTES_RAW + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int TX_BYTES = 2 * A_BYTES + 2 * W_BYTES_RAW;
+  static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
+  // One pipeline stage holds GROUP consecutive k-blocks (64 K-elements worth): with narrow channel counts a k-block
+  // is a single conv tap of 16 or 32 channels, and one barrier round trip per tap is what bounds the small-channel
+  // vocoder stages.  hi and lo planes of an operand arrive in ONE TMA box (plane dimension = 2).
+  static constexpr int GROUP = BLOCK_K >= 64 ? 1 : 64 / BLOCK_K;
+  static constexpr int SUB_BYTES = 2 * A_BYTES + 2 * W_BYTES;           // multiple of 1024 for every instantiation
+  static constexpr int STAGE_BYTES = GROUP * SUB_BYTES;
+  static constexpr int TX_BYTES = SUB_BYTES;                            // per k-block
   static constexpr int RAW_STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int NUM_STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int ACC_STAGES = 2;
+  // BLOCK_N = 256: the two epilogue warps of a TMEM lane quadrant split the columns of one tile (2 accumulator
+  // stages fill the 512 TMEM columns).  Narrower tiles: the two groups of 4 epilogue warps take ALTERNATE tiles and
+  // 4 accumulator stages keep the MMA warp ahead -- the per-tile epilogue latency chain (bias, TMEM load, global
+  // read-modify-write) of one group overlaps the other group's.
+  static constexpr bool SPLIT_COLS = BLOCK_N >= 256;
+  static constexpr int ACC_STAGES = SPLIT_COLS ? 2 : 4;
+  static constexpr int EPI_GROUPS = SPLIT_COLS ? 1 : 2;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BLOCK_N;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int SWIZZLE_BYTES = BLOCK_K * 2;                       // 128 / 64 / 32
   static constexpr uint32_t LAYOUT_TYPE = BLOCK_K == 64 ? 2u : BLOCK_K == 32 ? 4u : 6u;
   static constexpr uint32_t SBO = 8 * SWIZZLE_BYTES;
-  static constexpr int BIAS_FLOATS = (EPI == FD_EPI_GATE ? 3 : 1) * BLOCK_N;
+  static constexpr int BIAS_FLOATS = (EPI == FD_EPI_GATE ? 3 : 1) * BLOCK_N * EPI_GROUPS;
   // coalescing epilogue (LINEAR / RES_SKIP with >= 32 columns per warp): a 32x32 fp32 transpose scratch per warp
   static constexpr bool COALESCED = (EPI == FD_EPI_LINEAR || EPI == FD_EPI_RES_SKIP) && BLOCK_N >= 64;
   static constexpr int SCRATCH_BYTES = COALESCED ? (EPI_THREADS / 32) * 4096 : 0;
@@ -195,6 +205,8 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
   const int num_m_tiles = p.B * tiles_t;
   const int num_n_tiles = p.n_total / BLOCK_N;
   const int num_tiles = num_m_tiles * num_n_tiles;
+  int total_k_blocks = 0;
+  for (int sI = 0; sI < p.num_seg; ++sI) total_k_blocks += p.seg[sI].k_len / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_src0);
@@ -203,7 +215,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_THREADS / 32); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_THREADS / 32 / C::EPI_GROUPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -228,22 +240,23 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
         const int n_tile = (tile % num_n_tiles + m_tile) % num_n_tiles;
         const int b = m_tile / tiles_t, t0 = (m_tile % tiles_t) * BLOCK_M;
         const int n0 = n_tile * BLOCK_N;
-        int koff = 0;
-        for (int s = 0; s < p.num_seg; ++s) {
-          const FdSeg sg = p.seg[s];
-          const CUtensorMap* tm = sg.src == 0 ? &tm_src0 : &tm_src1;
-          for (int k0 = 0; k0 < sg.k_len; k0 += BLOCK_K) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = stage_base + stage * C::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], C::TX_BYTES);
-            tma_load_4d(st, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 0);
-            tma_load_4d(st + C::A_BYTES, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 1);
+        int s = 0, k0 = 0, koff = 0;                 // flattened (segment, k offset) iterator
+        for (int kb = 0; kb < total_k_blocks; kb += C::GROUP) {
+          const int nb = min(C::GROUP, total_k_blocks - kb);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], nb * C::TX_BYTES);
+          for (int g = 0; g < nb; ++g) {
+            const FdSeg sg = p.seg[s];
+            const CUtensorMap* tm = sg.src == 0 ? &tm_src0 : &tm_src1;
+            uint8_t* sub = st + g * C::SUB_BYTES;
+            tma_load_4d(sub, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 0);          // hi + lo planes
             const int kw = koff + k0 + p.w_kshift + (int)(b * p.w_bstride_k);
-            tma_load_3d(st + 2 * C::A_BYTES, &tm_w, &full_bar[stage], kw, n0, 0);
-            tma_load_3d(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w, &full_bar[stage], kw, n0, 1);
-            if (++stage == C::NUM_STAGES) { stage = 0; phase ^= 1; }
+            tma_load_3d(sub + 2 * C::A_BYTES, &tm_w, &full_bar[stage], kw, n0, 0);               // hi + lo planes
+            k0 += BLOCK_K;
+            if (k0 >= sg.k_len) { koff += sg.k_len; k0 = 0; ++s; }
           }
-          koff += sg.k_len;
+          if (++stage == C::NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -255,27 +268,28 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                              ((uint32_t)(BLOCK_M >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      int total_k_blocks = 0;
-      for (int s = 0; s < p.num_seg; ++s) total_k_blocks += p.seg[s].k_len / BLOCK_K;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < total_k_blocks; ++kb) {
+        for (int kb = 0; kb < total_k_blocks; kb += C::GROUP) {
+          const int nb = min(C::GROUP, total_k_blocks - kb);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(stage_base + stage * C::STAGE_BYTES);
-          const uint64_t a_hi = make_kmajor_desc(st, C::SBO, C::LAYOUT_TYPE);
-          const uint64_t a_lo = make_kmajor_desc(st + C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
-          const uint64_t w_hi = make_kmajor_desc(st + 2 * C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
-          const uint64_t w_lo = make_kmajor_desc(st + 2 * C::A_BYTES + C::W_BYTES, C::SBO, C::LAYOUT_TYPE);
+          for (int g = 0; g < nb; ++g) {
+            const uint32_t st = smem_u32(stage_base + stage * C::STAGE_BYTES + g * C::SUB_BYTES);
+            const uint64_t a_hi = make_kmajor_desc(st, C::SBO, C::LAYOUT_TYPE);
+            const uint64_t a_lo = make_kmajor_desc(st + C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
+            const uint64_t w_hi = make_kmajor_desc(st + 2 * C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
+            const uint64_t w_lo = make_kmajor_desc(st + 2 * C::A_BYTES + C::W_BYTES, C::SBO, C::LAYOUT_TYPE);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 elements * 2 B along K inside the swizzle row
-            // small terms first, the dominant hi*hi product last
-            umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-            umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 elements * 2 B along K inside the swizzle row
+              // small terms first, the dominant hi*hi product last
+              umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | g | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+              umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::NUM_STAGES) { stage = 0; phase ^= 1; }
@@ -288,12 +302,21 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
     // =========================================================== epilogue (8 warps)
     // warp w may access TMEM lanes [32*(w%4), +32); the two warps of a lane quadrant split the columns.
     const int q = warp % 4;
-    const int half = (warp - EPI_WARP0) / 4;
+    const int wgrp = (warp - EPI_WARP0) / 4;                 // 0 / 1: which set of four epilogue warps
+    const int half = C::SPLIT_COLS ? wgrp : 0;               // column half handled inside a shared tile
+    const int group = C::SPLIT_COLS ? 0 : wgrp;              // alternate-tile group
+    constexpr int GTHREADS = EPI_THREADS / C::EPI_GROUPS;    // threads cooperating on one tile
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - EPI_WARP0 * 32;   // 0..255
-    constexpr int HALVES = BLOCK_N >= 64 ? 2 : 1;
+    const int etid = (threadIdx.x - EPI_WARP0 * 32) % GTHREADS;
+    constexpr int HALVES = C::SPLIT_COLS ? 2 : 1;
+    float* const bias_g = bias_s + group * (C::BIAS_FLOATS / C::EPI_GROUPS);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (C::EPI_GROUPS == 2 && (it & 1) != group) {         // the other group's tile: just keep the stage counters
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int m_tile = tile / num_n_tiles;
         // rotate the column tile with the row tile: with a grid that is a multiple of num_n_tiles every CTA would
         // otherwise see the same n-tile forever, and epilogue costs differ per n-tile (residual vs skip columns)
@@ -303,22 +326,22 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
       const int t = t0 + row;
       const bool valid = t < p.T;
 
-      // stage the per-column bias vectors of this tile in shared memory
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // stage the per-column bias vectors of this tile in shared memory (named barrier of this tile's warps)
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
       if (EPI == FD_EPI_MAG) {
         // no bias
       } else if (EPI == FD_EPI_GATE) {
         const size_t bo = (size_t)b * p.gbias_bstride + n0;
-        for (int i = etid; i < BLOCK_N; i += EPI_THREADS) {
-          bias_s[i] = p.gbias_full[bo + i];
-          bias_s[BLOCK_N + i] = p.gbias_lo[bo + i];
-          bias_s[2 * BLOCK_N + i] = p.gbias_hi[bo + i];
+        for (int i = etid; i < BLOCK_N; i += GTHREADS) {
+          bias_g[i] = p.gbias_full[bo + i];
+          bias_g[BLOCK_N + i] = p.gbias_lo[bo + i];
+          bias_g[2 * BLOCK_N + i] = p.gbias_hi[bo + i];
         }
       } else {
-        for (int i = etid; i < BLOCK_N; i += EPI_THREADS)
-          bias_s[i] = p.bias ? p.bias[(size_t)b * p.bias_bstride + n0 + i] : 0.f;
+        for (int i = etid; i < BLOCK_N; i += GTHREADS)
+          bias_g[i] = p.bias ? p.bias[(size_t)b * p.bias_bstride + n0 + i] : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -326,7 +349,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
 
       if (EPI == FD_EPI_GATE || EPI == FD_EPI_MAG) {
         constexpr int HALF = BLOCK_N / 2;       // gate columns | filter columns
-        constexpr int PER = HALF / 2;           // gate columns handled by this warp
+        constexpr int PER = HALF / HALVES;      // gate columns handled by this warp
         const int cb = half * PER;
         for (int c = 0; c < PER; c += 16) {
           const int c0 = cb + c;
@@ -345,9 +368,9 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
               if (EPI == FD_EPI_MAG)
                 fd_epi_mag<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8);
               else
-                fd_epi_gate<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8, bias_s + cc, bias_s + HALF + cc,
-                               bias_s + BLOCK_N + cc, bias_s + BLOCK_N + HALF + cc, bias_s + 2 * BLOCK_N + cc,
-                               bias_s + 2 * BLOCK_N + HALF + cc);
+                fd_epi_gate<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8, bias_g + cc, bias_g + HALF + cc,
+                               bias_g + BLOCK_N + cc, bias_g + BLOCK_N + HALF + cc, bias_g + 2 * BLOCK_N + cc,
+                               bias_g + 2 * BLOCK_N + HALF + cc);
             }
           }
         }
@@ -357,7 +380,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
         //      before the TMEM wait (latency overlap); per-item math is the shared V=4 epilogue of fd_common.cuh order.
         constexpr int PER = BLOCK_N / HALVES;
         const uint32_t my_scratch = smem_u32(scratch_s) + (warp - EPI_WARP0) * 4096;
-        const uint32_t bias_addr = smem_u32(bias_s);
+        const uint32_t bias_addr = smem_u32(bias_g);
         const int j4 = (lane & 7) * 4, rsub = lane >> 3;
         const int rbase = t0 + q * 32 + rsub;            // time index of pass 0
         for (int c = 0; c < PER; c += 32) {
@@ -507,8 +530,8 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v8[i] = v[h * 8 + i];
                 const int cc = col + h * 8;
-                if (EPI == FD_EPI_LINEAR) fd_epi_linear<8, PREC>(p, b, t, n0 + cc, v8, bias_s, n0);
-                else fd_epi_res_skip<8, PREC>(p, b, t, n0 + cc, v8, bias_s + cc);
+                if (EPI == FD_EPI_LINEAR) fd_epi_linear<8, PREC>(p, b, t, n0 + cc, v8, bias_g, n0);
+                else fd_epi_res_skip<8, PREC>(p, b, t, n0 + cc, v8, bias_g + cc);
               }
             }
           }
@@ -561,7 +584,7 @@ int make_src_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, long 
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B, 2};
   cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)bs * 2, (cuuint64_t)ps * 2};
-  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)BLOCK_M, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)BLOCK_M, 1, 2};   // both planes in one box
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -576,7 +599,7 @@ int make_w_map(CUtensorMap* m, const uint16_t* ptr, int N, int K, int block_n, i
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
-  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)block_n, 1};
+  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)block_n, 2};      // both planes in one box
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
