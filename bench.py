@@ -254,7 +254,7 @@ def main():
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "traffic": None, "algorithmic_flops_per_launch": g1_flops, "avg_launch_ms": t1 * 1e3,
-                "mma_flops_per_launch": 3 * g1_flops if backend_name == "tc" else None,
+                "mma_flops_per_launch": (1 if args.precision.lower().endswith("x1") else 3) * g1_flops if backend_name == "tc" else None,
                 "note": "fp32 parity is emulated with 3 fp16 tensor-core products per algorithmic product; "
                         "tensor-pipe utilisation is ~3x frac",
                 "block": {"gemm2_avg_launch_ms": t2 * 1e3, "block_tflops": (g1_flops + g2_flops) / (t1 + t2) / 1e12,
@@ -326,6 +326,35 @@ def main():
         except Exception as ex:  # noqa: BLE001
             unipc = {"error": repr(ex)[:300]}
 
+    # ---- single-product GEMM mode (hi planes only: half-precision operands, fp32 accumulation): the same sampler run
+    #      with the same Philox seed, timed, and its output deviation from the headline (22-bit) path reported
+    x1 = None
+    single = args.precision.lower().endswith("x1")
+    if not args.no_vocoder and not single:
+        try:
+            d2 = DIFFUSIONS.build(dict(
+                type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", backend=args.backend,
+                                                        precision=args.precision + "x1", **WN_CFG),
+                mel_channels=M, noise_schedule="linear", timesteps=TIMESTEPS, max_beta=0.01, sampler_interval=interval,
+                spec_min=[-5.0], spec_max=[0.0], noise_predictor="naive")).to(dev).eval()
+            d2.denoise_fn.load_state_dict(diff.denoise_fn.state_dict())
+            ref_mel = diff(feats, sampler_interval=interval, noise_predictor="naive", seed=77)
+            d2(feats, sampler_interval=interval, noise_predictor="naive", seed=77)
+            barrier()
+            ev0.record()
+            x1_mel = d2(feats, sampler_interval=interval, noise_predictor="naive", seed=77)
+            ev1.record()
+            barrier()
+            x_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
+            num = float((x1_mel - ref_mel).double().norm()); den = float(ref_mel.double().norm())
+            x1 = {"precision": args.precision + "x1", "ms_per_step": x_ms, "mel_frames_per_sec": world * B * T / (x_ms * 1e-3),
+                  "sampler_output_rel_l2_vs_headline": num / den,
+                  "sampler_output_max_abs_diff": float((x1_mel - ref_mel).abs().max()),
+                  "what": "same sampler, same Philox seed, one tensor-core product per k-step (11-bit operand mantissa)"}
+            del d2, ref_mel, x1_mel
+        except Exception as ex:  # noqa: BLE001
+            x1 = {"error": repr(ex)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = cpu_baseline_sample(1000, 1)
@@ -337,7 +366,8 @@ def main():
             "metric": "mel_frames_per_sec_100step_ddpm", "value": value, "unit": "mel-frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (3x fp16 split-product tcgen05, fp32 accumulate)" if backend_name == "tc" else "f32 (SIMT)",
+            "dtype": ("f16 operands, fp32 accumulate (single tcgen05 product)" if single else
+                      "f32 (3x fp16 split-product tcgen05, fp32 accumulate)") if backend_name == "tc" else "f32 (SIMT)",
             "data": "synthetic",
             "config": {"workload": f"svc_content_vec: WaveNet(128,256,512,L20) {args.evals}-eval DDPM (naive) sampler, "
                                    f"timesteps=1000 interval={interval}",
@@ -345,7 +375,7 @@ def main():
                        "backend": backend_name, "precision": args.precision,
                        "l2": "inputs (features 131 MB + weights 420 MB + 1 GB activations per layer) larger than L2"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "vocoder": voc, "unipc": unipc, "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
+            "vocoder": voc, "unipc": unipc, "single_product": x1, "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
         }
         print(json.dumps(line))
     if world > 1:

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfishdiff_b200.so")
 
 PREC_F16, PREC_BF16 = 0, 1
+PREC_SINGLE = 0x10   # or-ed into the prec of GEMM calls: one product over the hi planes
 BACKEND_TC, BACKEND_SIMT = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 ABI_VERSION = 1
@@ -147,12 +148,22 @@ def launch_count() -> int:
 
 
 def prec_code(precision: str) -> int:
+    """Storage precision of the split planes: 'f16' / 'bf16' (an 'x1' suffix only changes the GEMM arithmetic)."""
     p = precision.lower()
+    if p.endswith("x1"):
+        p = p[:-2]
     if p in ("f16", "fp16", "half"):
         return PREC_F16
     if p in ("bf16", "bfloat16"):
         return PREC_BF16
-    raise ValueError(f"unknown precision {precision!r} (use 'f16' or 'bf16')")
+    raise ValueError(f"unknown precision {precision!r} (use 'f16', 'bf16', 'f16x1' or 'bf16x1')")
+
+
+def mma_code(precision: str) -> int:
+    """`prec` argument of the GEMM entry points: 'f16' / 'bf16' multiply the split planes with three tensor-core
+    products (22- / 16-bit operand mantissas); 'f16x1' / 'bf16x1' multiply the hi planes only (one product: plain
+    half-precision operands, fp32 accumulation -- the arithmetic class of torch autocast / TF32 convolutions)."""
+    return prec_code(precision) | (PREC_SINGLE if precision.lower().endswith("x1") else 0)
 
 
 def backend_code(backend: str) -> int:

@@ -10,6 +10,7 @@ namespace {
 thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
 
+void set_prec(FdTapGemm& p, int prec) { p.prec = prec & 0xF; p.single = (prec & FD_SINGLE) ? 1 : 0; }
 void init_desc(FdTapGemm& p) { memset(&p, 0, sizeof(p)); p.acc_scale = 1.f; p.post_scale = 1.f; p.planes_scale = 1.f; p.res_scale = 1.f; }
 
 void set_src(FdTapGemm& p, int i, const uint16_t* ptr, int C) {
@@ -149,7 +150,7 @@ static int wavenet_block(const uint16_t* x_planes, uint16_t* x_out_planes, const
   // ---- GEMM1: dilated conv (3 taps) + conditioner projection + gate
   FdTapGemm p;
   init_desc(p);
-  p.B = B; p.T = T; p.prec = prec;
+  p.B = B; p.T = T; set_prec(p, prec);
   p.n_total = 2 * C; p.k_total = 3 * C + E; p.num_seg = 4;
   p.seg[0] = FdSeg{0, -dilation, 0, C};
   p.seg[1] = FdSeg{0, 0, 0, C};
@@ -168,7 +169,7 @@ static int wavenet_block(const uint16_t* x_planes, uint16_t* x_out_planes, const
   // ---- GEMM2: output projection + residual / skip
   FdTapGemm q;
   init_desc(q);
-  q.B = B; q.T = T; q.prec = prec;
+  q.B = B; q.T = T; set_prec(q, prec);
   q.n_total = 2 * C; q.k_total = C; q.num_seg = 1;
   q.seg[0] = FdSeg{0, 0, 0, C};
   set_src(q, 0, z_planes, C);
@@ -186,7 +187,7 @@ int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream) {
   FD_REQUIRE(d->B > 0 && d->T > 0 && d->Cin > 0 && d->N > 0, "fd_conv_cl_fwd: bad shape");
   FdTapGemm p;
   init_desc(p);
-  p.B = d->B; p.T = d->T; p.prec = d->prec;
+  p.B = d->B; p.T = d->T; set_prec(p, d->prec);
   p.n_total = d->N; p.k_total = d->ntaps * d->Cin; p.num_seg = d->ntaps;
   for (int j = 0; j < d->ntaps; ++j) p.seg[j] = FdSeg{0, d->shifts[j], 0, d->Cin};
   set_src(p, 0, d->in_planes, d->Cin);
@@ -209,7 +210,7 @@ int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag
   FD_REQUIRE((long long)(frames - 1) * hop + n_fft <= Np, "fd_stft_mag_fwd: frames exceed the padded signal");
   FdTapGemm p;
   init_desc(p);
-  p.B = B; p.T = frames; p.prec = prec;
+  p.B = B; p.T = frames; set_prec(p, prec);
   p.n_total = 2 * NB; p.k_total = n_fft; p.num_seg = 1;
   p.seg[0] = FdSeg{0, 0, 0, n_fft};
   p.src[0] = padded; p.src_C[0] = n_fft;
@@ -226,7 +227,7 @@ int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream) {
   FD_REQUIRE(d->B > 0 && d->T > 0 && d->n_total > 0 && d->k_total > 0, "fd_gemm_cl_fwd: bad shape");
   FdTapGemm p;
   init_desc(p);
-  p.B = d->B; p.T = d->T; p.prec = d->prec;
+  p.B = d->B; p.T = d->T; set_prec(p, d->prec);
   p.n_total = d->n_total; p.k_total = d->k_total; p.num_seg = d->num_seg;
   for (int j = 0; j < d->num_seg; ++j) {
     FD_REQUIRE(d->seg_src[j] == 0 || d->seg_src[j] == 1, "fd_gemm_cl_fwd: segment %d has bad source", j);

@@ -15,6 +15,8 @@
 
 #define FD_F16 0
 #define FD_BF16 1
+// flag or-ed into a `prec` argument of the GEMM entry points: multiply the hi planes only (one product)
+#define FD_SINGLE 0x10
 
 #define FD_MAX_SEG 16
 
@@ -43,6 +45,7 @@ struct FdTapGemm {
   int k_total;   // sum of seg.k_len (row pitch of W)
   int num_seg;
   int prec;      // FD_F16 / FD_BF16
+  int single;    // 1: one product over the hi planes (half-precision operands), 0: three split products
   FdSeg seg[FD_MAX_SEG];
   const uint16_t* src[2];   // split planes [2][B][T][src_C]
   int src_C[2];
@@ -191,6 +194,17 @@ __device__ __forceinline__ void fd_load_planes(const uint16_t* planes, size_t pl
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) y[i] = fd_combine(hi[i], lo[i], prec);
+}
+
+// hi plane only (single-product mode of the SIMT twin)
+__device__ __forceinline__ void fd_load_hi8(const uint16_t* planes, size_t off, float (&y)[8], int prec) {
+  const uint4 a = *reinterpret_cast<const uint4*>(planes + off);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    y[2 * i] = fd_h2f((uint16_t)(w[i] & 0xffff), prec);
+    y[2 * i + 1] = fd_h2f((uint16_t)(w[i] >> 16), prec);
+  }
 }
 
 // register-level (un)packing of 8 consecutive channels; used by the split-phase (prefetch / finish) epilogues

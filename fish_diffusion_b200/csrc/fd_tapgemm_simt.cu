@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) fd_tapgemm_simt_kernel(const FdTapGemm p)
         const int kk = k0 + kh * 8;
         if (t >= 0 && t < p.T && t0 + row < p.T && kk < sg.k_len) {
           const size_t off = (size_t)b * a_bs + (size_t)t * a_rs + sg.c_off + kk;
-          fd_load_planes<8>(src, a_plane, off, v, p.prec);
+          if (p.single) fd_load_hi8(src, off, v, p.prec);
+          else fd_load_planes<8>(src, a_plane, off, v, p.prec);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -79,13 +80,16 @@ __global__ void __launch_bounds__(256) fd_tapgemm_simt_kernel(const FdTapGemm p)
         if (n < p.n_total && kk < sg.k_len) {
           const long long kw = (long long)koff + kk + p.w_kshift + (long long)b * p.w_bstride_k;
           if (p.w_kshift == 0 && p.w_bstride_k == 0) {
-            fd_load_planes<8>(p.w, w_plane, (size_t)n * p.k_total + kw, v, p.prec);
+            if (p.single) fd_load_hi8(p.w, (size_t)n * p.k_total + kw, v, p.prec);
+            else fd_load_planes<8>(p.w, w_plane, (size_t)n * p.k_total + kw, v, p.prec);
           } else {   // weight-gradient mode: unaligned / out-of-range K coordinates read as zero (like the TMA box)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const long long ki = kw + i;
               v[i] = (ki >= 0 && ki < p.k_total)
-                         ? fd_combine(p.w[(size_t)n * p.k_total + ki], p.w[w_plane + (size_t)n * p.k_total + ki], p.prec)
+                         ? (p.single ? fd_h2f(p.w[(size_t)n * p.k_total + ki], p.prec)
+                                     : fd_combine(p.w[(size_t)n * p.k_total + ki],
+                                                  p.w[w_plane + (size_t)n * p.k_total + ki], p.prec))
                          : 0.f;
             }
           }

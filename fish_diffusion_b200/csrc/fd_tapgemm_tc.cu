@@ -148,7 +148,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   return d;
 }
 
-template <int BLOCK_N, int BLOCK_K, int EPI>
+// NPL = operand planes staged per k-block: 2 (hi + lo, three products) or 1 (hi only, one product: 11-bit (f16) /
+// 8-bit (bf16) operand mantissas, the arithmetic of a plain half-precision tensor-core GEMM with fp32 accumulation).
+template <int BLOCK_N, int BLOCK_K, int EPI, int NPL>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -156,7 +158,7 @@ struct Cfg {
   // is a single conv tap of 16 or 32 channels, and one barrier round trip per tap is what bounds the small-channel
   // vocoder stages.  hi and lo planes of an operand arrive in ONE TMA box (plane dimension = 2).
   static constexpr int GROUP = BLOCK_K >= 64 ? 1 : 64 / BLOCK_K;
-  static constexpr int SUB_BYTES = 2 * A_BYTES + 2 * W_BYTES;           // multiple of 1024 for every instantiation
+  static constexpr int SUB_BYTES = NPL * (A_BYTES + W_BYTES);           // multiple of 1024 for every instantiation
   static constexpr int STAGE_BYTES = GROUP * SUB_BYTES;
   static constexpr int TX_BYTES = SUB_BYTES;                            // per k-block
   static constexpr int RAW_STAGES = (200 * 1024) / STAGE_BYTES;
@@ -182,11 +184,11 @@ struct Cfg {
                                     (2 * NUM_STAGES + 2 * ACC_STAGES) * 8 + 16 + SCRATCH_BYTES;
 };
 
-template <int BLOCK_N, int BLOCK_K, int EPI, int PREC>
+template <int BLOCK_N, int BLOCK_K, int EPI, int PREC, int NPL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                      const __grid_constant__ CUtensorMap tm_w, const FdTapGemm p) {
-  using C = Cfg<BLOCK_N, BLOCK_K, EPI>;
+  using C = Cfg<BLOCK_N, BLOCK_K, EPI, NPL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -252,7 +254,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
             uint8_t* sub = st + g * C::SUB_BYTES;
             tma_load_4d(sub, tm, &full_bar[stage], sg.c_off + k0, t0 + sg.shift, b, 0);          // hi + lo planes
             const int kw = koff + k0 + p.w_kshift + (int)(b * p.w_bstride_k);
-            tma_load_3d(sub + 2 * C::A_BYTES, &tm_w, &full_bar[stage], kw, n0, 0);               // hi + lo planes
+            tma_load_3d(sub + NPL * C::A_BYTES, &tm_w, &full_bar[stage], kw, n0, 0);               // hi + lo planes
             k0 += BLOCK_K;
             if (k0 >= sg.k_len) { koff += sg.k_len; k0 = 0; ++s; }
           }
@@ -280,15 +282,19 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
             const uint32_t st = smem_u32(stage_base + stage * C::STAGE_BYTES + g * C::SUB_BYTES);
             const uint64_t a_hi = make_kmajor_desc(st, C::SBO, C::LAYOUT_TYPE);
             const uint64_t a_lo = make_kmajor_desc(st + C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
-            const uint64_t w_hi = make_kmajor_desc(st + 2 * C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
-            const uint64_t w_lo = make_kmajor_desc(st + 2 * C::A_BYTES + C::W_BYTES, C::SBO, C::LAYOUT_TYPE);
+            const uint64_t w_hi = make_kmajor_desc(st + NPL * C::A_BYTES, C::SBO, C::LAYOUT_TYPE);
+            const uint64_t w_lo = make_kmajor_desc(st + NPL * C::A_BYTES + C::W_BYTES, C::SBO, C::LAYOUT_TYPE);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 elements * 2 B along K inside the swizzle row
-              // small terms first, the dominant hi*hi product last
-              umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | g | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
-              umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+              if (NPL == 2) {
+                // small terms first, the dominant hi*hi product last
+                umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (kb | g | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1u);
+              } else {
+                umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | g | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -579,12 +585,12 @@ CUtensorMapSwizzle swizzle_for(int block_k) {
 }
 
 int make_src_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, long long rs, long long bs,
-                 long long ps, int block_k) {
+                 long long ps, int block_k, int npl) {
   PFN_tmapEncodeTiled enc = get_encode();
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B, 2};
   cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)bs * 2, (cuuint64_t)ps * 2};
-  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)BLOCK_M, 1, 2};   // both planes in one box
+  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)BLOCK_M, 1, (cuuint32_t)npl};   // planes in one box
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -594,12 +600,12 @@ int make_src_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, long 
   return 0;
 }
 
-int make_w_map(CUtensorMap* m, const uint16_t* ptr, int N, int K, int block_n, int block_k) {
+int make_w_map(CUtensorMap* m, const uint16_t* ptr, int N, int K, int block_n, int block_k, int npl) {
   PFN_tmapEncodeTiled enc = get_encode();
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
-  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)block_n, 2};      // both planes in one box
+  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)block_n, (cuuint32_t)npl};   // planes in one box
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -611,27 +617,26 @@ int make_w_map(CUtensorMap* m, const uint16_t* ptr, int N, int K, int block_n, i
 
 int g_num_sms = 0;
 
-template <int BLOCK_N, int BLOCK_K, int EPI>
-int launch_cfg(const FdTapGemm& p, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, BLOCK_K, EPI>;
+template <int BLOCK_N, int BLOCK_K, int EPI, int PREC, int NPL>
+int launch_inst(const FdTapGemm& p, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, BLOCK_K, EPI, NPL>;
   CUtensorMap tm0, tm1, tmw;
-  int rc = make_src_map(&tm0, p.src[0], p.B, p.T, p.src_C[0], p.src_rs[0], p.src_bs[0], p.src_ps[0], BLOCK_K);
+  int rc = make_src_map(&tm0, p.src[0], p.B, p.T, p.src_C[0], p.src_rs[0], p.src_bs[0], p.src_ps[0], BLOCK_K, NPL);
   if (rc) return rc;
   if (p.src[1] != nullptr) {
-    rc = make_src_map(&tm1, p.src[1], p.B, p.T, p.src_C[1], p.src_rs[1], p.src_bs[1], p.src_ps[1], BLOCK_K);
+    rc = make_src_map(&tm1, p.src[1], p.B, p.T, p.src_C[1], p.src_rs[1], p.src_bs[1], p.src_ps[1], BLOCK_K, NPL);
     if (rc) return rc;
   } else {
     tm1 = tm0;
   }
-  rc = make_w_map(&tmw, p.w, p.n_total, p.k_total, BLOCK_N, BLOCK_K);
+  rc = make_w_map(&tmw, p.w, p.n_total, p.k_total, BLOCK_N, BLOCK_K, NPL);
   if (rc) return rc;
 
-  auto kern = p.prec == FD_F16 ? fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI, FD_F16>
-                               : fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI, FD_BF16>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[p.prec == FD_F16 ? 0 : 1]) {
+  auto kern = fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI, PREC, NPL>;
+  static bool attr_set = false;
+  if (!attr_set) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set[p.prec == FD_F16 ? 0 : 1] = true;
+    attr_set = true;
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -644,6 +649,16 @@ int launch_cfg(const FdTapGemm& p, cudaStream_t stream) {
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tmw, p);
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BLOCK_N, int BLOCK_K, int EPI>
+int launch_cfg(const FdTapGemm& p, cudaStream_t stream) {
+  if (p.single) {
+    return p.prec == FD_F16 ? launch_inst<BLOCK_N, BLOCK_K, EPI, FD_F16, 1>(p, stream)
+                            : launch_inst<BLOCK_N, BLOCK_K, EPI, FD_BF16, 1>(p, stream);
+  }
+  return p.prec == FD_F16 ? launch_inst<BLOCK_N, BLOCK_K, EPI, FD_F16, 2>(p, stream)
+                          : launch_inst<BLOCK_N, BLOCK_K, EPI, FD_BF16, 2>(p, stream);
 }
 
 template <int BLOCK_N, int BLOCK_K>

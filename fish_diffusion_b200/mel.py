@@ -156,10 +156,10 @@ class PitchAdjustableMelSpectrogram:
         mag = torch.empty((2, B, frames, self.NB), dtype=torch.int16, device=dev)
         mag_scale = 1.0 if key_shift == 0 else float(self.win_size) / float(win_new)
         N.check(lib.fd_stft_mag_fwd(N.ptr(padded), N.ptr(w_planes), N.ptr(mag), B, np_arg, kpad, hop, frames, self.NB,
-                                    w_inv, mag_scale, prec, self._backend(), st), "fd_stft_mag_fwd")
+                                    w_inv, mag_scale, N.mma_code(self.precision), self._backend(), st), "fd_stft_mag_fwd")
         mw, mw_inv = self._mel_weights(bins, dev, prec)
         mel_cl = torch.empty((B, frames, self.n_mels), dtype=torch.float32, device=dev)
-        N.conv_cl(mag, mw, B, frames, self.NB, self.n_mels, [0], out_f32=mel_cl, w_inv_scale=mw_inv, prec=prec,
+        N.conv_cl(mag, mw, B, frames, self.NB, self.n_mels, [0], out_f32=mel_cl, w_inv_scale=mw_inv, prec=N.mma_code(self.precision),
                   backend=self._backend())
         out = torch.empty((B, self.n_mels, frames), dtype=torch.float32, device=dev)
         N.check(lib.fd_transpose_nwc_to_ncw(N.ptr(mel_cl), N.ptr(out), B, frames, self.n_mels, st),

@@ -200,7 +200,7 @@ class Generator(nn.Module):
             return self._pack
         prec = N.prec_code(self.precision)
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
-        pk = {"prec": prec, "pre": self._pack_conv(self.conv_pre, prec, device), "ups": [], "src": [], "res": []}
+        pk = {"prec": prec, "mma": N.mma_code(self.precision), "pre": self._pack_conv(self.conv_pre, prec, device), "ups": [], "src": [], "res": []}
         for i, up in enumerate(self.ups):
             pk["ups"].append(self._pack_convt(up, prec, device))
             nc = self.noise_convs[i]
@@ -224,7 +224,7 @@ class Generator(nn.Module):
     # ------------------------------------------------------------------------------------ forward
     def _conv(self, pc, in_planes, B, T, **kw):
         N.conv_cl(in_planes, pc["w"], B, T, pc["Ci"], pc["N"], pc["shifts"], bias=pc["bias"], w_inv_scale=pc["inv"],
-                  prec=self._pack["prec"], backend=pc["backend"], **kw)
+                  prec=self._pack["mma"], backend=pc["backend"], **kw)
 
     @torch.no_grad()
     def source(self, f0, S_hop, rand_ini=None, sine_noise=None, seed=None):

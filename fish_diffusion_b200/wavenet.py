@@ -82,7 +82,8 @@ class WaveNet(nn.Module):
     """WaveNet denoiser (reference wavenet.py:151-236) on sm_100a kernels.
 
     Extra keyword arguments (not in the reference, defaults keep reference configs working):
-      precision: "f16" (22-bit split planes, fp32-faithful) or "bf16" (16-bit split planes, fp32 range)
+      precision: "f16" (22-bit split planes, fp32-faithful) or "bf16" (16-bit split planes, fp32 range); "f16x1" /
+        "bf16x1" keep that storage but multiply the hi planes only (one tensor-core product, half-precision operands)
       backend:   "auto" (tcgen05 when the shape has a tensor-core instantiation, else the SIMT twin), "tc", "simt"
     """
 
@@ -151,7 +152,7 @@ class WaveNet(nn.Module):
         def pack(w2d, sc):
             return N.pack_weight(w2d, prec, sc), 1.0 / sc
 
-        pk = {"prec": prec, "gate_tile": gate_tile, "backend": self._resolve_backend(), "perm": perm,
+        pk = {"prec": prec, "mma": N.mma_code(self.precision), "gate_tile": gate_tile, "backend": self._resolve_backend(), "perm": perm,
               "s_in": s_in, "s_skip": s_skip, "s_out": s_out, "s1": s1, "s2": s2}
         pk["w_in"], pk["w_in_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0], s_in)
         pk["b_in"] = f32(self.input_projection.conv.bias).contiguous()
@@ -263,7 +264,7 @@ class WaveNet(nn.Module):
         C, E, L = self.residual_channels, self.d_encoder, self.n_layers
         assert M == self.mel_channels and tuple(cond_planes.shape) == (2, B, T, E)
         pk = self._packed(dev)
-        prec, backend = pk["prec"], pk["backend"]
+        mma, backend = pk["mma"], pk["backend"]
         steps = steps.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         Bs = steps.numel()
         if Bs not in (1, B):
@@ -285,7 +286,7 @@ class WaveNet(nn.Module):
                                          N.ptr(ws["gb_ws"]), L, Bs, C, 3 * C + E, st), "fd_wavenet_gate_bias")
         # head: relu(input_projection(x)) with masked rows zeroed (wavenet.py:211-218)
         N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], row_mask=x_mask, out_planes=ws["xr"],
-                  w_inv_scale=pk["w_in_inv"], act=N.ACT_RELU, prec=prec, backend=backend)
+                  w_inv_scale=pk["w_in_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
         gb_stride = 2 * C if Bs > 1 else 0
         skip_scale = 1.0 / math.sqrt(L)
         for l in range(L):
@@ -294,12 +295,12 @@ class WaveNet(nn.Module):
                 N.ptr(ws["xr"]), N.ptr(cond_planes), N.ptr(ws["z"]), N.ptr(pk["w1"][l]), N.ptr(pk["w2"][l]),
                 N.ptr(gb[0, l]), N.ptr(gb[1, l]), N.ptr(gb[2, l]), gb_stride, N.ptr(pk["b2"][l]),
                 N.ptr(ws["skip_f32"]), N.ptr(ws["skip_planes"]), skip_scale, B, T, C, E, pk["dil"][l],
-                pk["gate_tile"], pk["w1_inv"][l], pk["w2_inv"][l], flags, prec, backend, st), "fd_wavenet_block_fwd")
+                pk["gate_tile"], pk["w1_inv"][l], pk["w2_inv"][l], flags, mma, backend, st), "fd_wavenet_block_fwd")
         # tail: relu(skip_projection(sum/sqrt(L))) -> output_projection (+ mask) (wavenet.py:228-234)
         N.conv_cl(ws["skip_planes"], pk["w_skip"], B, T, C, C, [0], bias=pk["b_skip"], out_planes=ws["z"],
-                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=prec, backend=backend)
+                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
         N.conv_cl(ws["z"], pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], row_mask=x_mask, out_f32=out,
-                  w_inv_scale=pk["w_out_inv"], prec=prec, backend=backend)
+                  w_inv_scale=pk["w_out_inv"], prec=mma, backend=backend)
         return out
 
     def forward(self, x, diffusion_step, conditioner, x_masks=None, cond_masks=None):

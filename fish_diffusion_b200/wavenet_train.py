@@ -69,7 +69,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         C, E, L = net.residual_channels, net.d_encoder, net.n_layers
         Bs = d.shape[0]
         pk = net._packed(dev)                       # forward packs (re-made whenever a parameter version changes)
-        prec, backend = pk["prec"], pk["backend"]
+        prec, mma, backend = pk["prec"], pk["mma"], pk["backend"]
         lib, st = N.lib(), N.stream_ptr(dev)
         i16 = dict(dtype=torch.int16, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -89,7 +89,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         h_planes = torch.empty((2, B, T, C), **i16)
         eps = torch.empty((B, T, M), **f32)
         N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], out_planes=xs[0], w_inv_scale=pk["w_in_inv"],
-                  act=N.ACT_RELU, prec=prec, backend=backend)
+                  act=N.ACT_RELU, prec=mma, backend=backend)
         gb_stride = 2 * C if Bs > 1 else 0
         for l in range(L):
             flags = (1 if l == 0 else 0) | (2 if l == L - 1 else 0)
@@ -97,11 +97,11 @@ class WaveNetTrainFn(torch.autograd.Function):
                 N.ptr(xs[l]), N.ptr(xs[l + 1]), N.ptr(cond_planes), N.ptr(z), N.ptr(ys[l]), N.ptr(pk["w1"][l]),
                 N.ptr(pk["w2"][l]), N.ptr(gb[0, l]), N.ptr(gb[1, l]), N.ptr(gb[2, l]), gb_stride, N.ptr(pk["b2"][l]),
                 N.ptr(skip_f32), N.ptr(s_planes), 1.0 / math.sqrt(L), B, T, C, E, pk["dil"][l], pk["gate_tile"],
-                pk["w1_inv"][l], pk["w2_inv"][l], flags, prec, backend, st), "fd_wavenet_block_fwd_train")
+                pk["w1_inv"][l], pk["w2_inv"][l], flags, mma, backend, st), "fd_wavenet_block_fwd_train")
         N.conv_cl(s_planes, pk["w_skip"], B, T, C, C, [0], bias=pk["b_skip"], out_planes=h_planes,
-                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=prec, backend=backend)
+                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
         N.conv_cl(h_planes, pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], out_f32=eps, w_inv_scale=pk["w_out_inv"],
-                  prec=prec, backend=backend)
+                  prec=mma, backend=backend)
         ctx.net = net
         ctx.saved = dict(x_planes=x_planes, cond_planes=cond_planes, d=d, xs=xs, ys=ys, s_planes=s_planes,
                          h_planes=h_planes, shape=(B, T, M, Bs))
@@ -116,7 +116,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         dev = d_eps.device
         pk = net._packed(dev)
         bw = _bwd_packs(net, pk, dev)
-        prec, pref = pk["prec"], pk["backend"]
+        prec, mma, pref = pk["prec"], pk["mma"], pk["backend"]
         perm, gate_tile = pk["perm"], pk["gate_tile"]
         lib, st = N.lib(), N.stream_ptr(dev)
         i16 = dict(dtype=torch.int16, device=dev)
@@ -153,7 +153,7 @@ class WaveNetTrainFn(torch.autograd.Function):
             """sum_{b,t} rows[b,t,r] * cols[b,t,c] / S  -> fp32 [R, Cc]  (per-item partials, then one reduction)"""
             part = torch.empty((B, R, Cc), **f32)
             N.gemm_cl(rowsT, Tp, colsT, Cc, B * Tp, B, R, [(0, 0, 0, Tp)], strides0=(B * Tp, Tp, R * B * Tp),
-                      w_bstride_k=Tp, out_f32=part, prec=prec, backend=_backend_for(pref, Cc, Tp, 1))
+                      w_bstride_k=Tp, out_f32=part, prec=mma, backend=_backend_for(pref, Cc, Tp, 1))
             out = torch.empty((R, Cc), **f32)
             N.check(lib.fd_reduce_batch(N.ptr(part), N.ptr(out), B, R * Cc, inv_S, st), "fd_reduce_batch")
             return out
@@ -166,7 +166,7 @@ class WaveNetTrainFn(torch.autograd.Function):
             return out
 
         def dgrad(src0, C0, w, w_inv, n_total, k_total, segs, **kw):
-            N.gemm_cl(src0, C0, w, n_total, k_total, B, T, segs, w_inv_scale=w_inv, prec=prec,
+            N.gemm_cl(src0, C0, w, n_total, k_total, B, T, segs, w_inv_scale=w_inv, prec=mma,
                       backend=_backend_for(pref, n_total, segs[0][3], len(segs)), **kw)
 
         grads = {}
@@ -210,10 +210,10 @@ class WaveNetTrainFn(torch.autograd.Function):
             dil = pk["dil"][l]
             if dx_next is None:     # K offset C selects the skip half of W2^T (aligned: C % 8 == 0)
                 N.gemm_cl(dskip_planes, C, bw["w2t"][l], C, 2 * C, B, T, [(0, 0, 0, C)], w_kshift=C, out_f32=dz,
-                          w_inv_scale=bw["w2t_inv"][l], prec=prec, backend=_backend_for(pref, C, C, 1))
+                          w_inv_scale=bw["w2t_inv"][l], prec=mma, backend=_backend_for(pref, C, C, 1))
             else:
                 N.gemm_cl(dx_next, C, bw["w2t"][l], C, 2 * C, B, T, [(0, 0, 0, C), (1, 0, 0, C)], src1=dskip_planes,
-                          C1=C, out_f32=dz, w_inv_scale=bw["w2t_inv"][l], prec=prec,
+                          C1=C, out_f32=dz, w_inv_scale=bw["w2t_inv"][l], prec=mma,
                           backend=_backend_for(pref, C, C, 2))
             N.check(lib.fd_gate_bwd(N.ptr(dz), N.ptr(sv["ys"][l]), N.ptr(dy), rows, C, gate_tile, prec, st), "fd_gate_bwd")
             # ---- weight gradient of the output projection: rows [residual | skip] x z

@@ -26,6 +26,10 @@ extern "C" {
 
 #define FD_PREC_F16 0
 #define FD_PREC_BF16 1
+/* or-ed into the `prec` of a GEMM entry point (fd_wavenet_block_fwd*, fd_conv_cl_fwd, fd_gemm_cl_fwd,
+ * fd_stft_mag_fwd): multiply the hi planes only -- one tensor-core product per k-step instead of three, i.e. plain
+ * half-precision operands (11-bit / 8-bit mantissa) with fp32 accumulation.  Storage stays two planes. */
+#define FD_PREC_SINGLE 0x10
 #define FD_BACKEND_TC 0
 #define FD_BACKEND_SIMT 1
 #define FD_ABI_VERSION 1

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check-ddp", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced network (tests)")
+    ap.add_argument("--precision", default="f16", help="f16 | bf16 (three split products) or f16x1 | bf16x1 (one product)")
     ap.add_argument("--fp16-hook", action="store_true", help="use the reference's fp16_compress_hook")
     args = ap.parse_args()
     import __graft_entry__ as ge
@@ -51,6 +52,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cfg = dict(WN_CFG, residual_channels=128, d_encoder=64, mel_channels=64, residual_layers=3) if args.small else WN_CFG
+    cfg = dict(cfg, precision=args.precision)
     B, T, M, E = args.batch, args.frames, cfg["mel_channels"], cfg["d_encoder"]
     g = torch.Generator().manual_seed(100)
     feats_all = torch.randn(world * B, T, E, generator=g)
@@ -113,7 +115,7 @@ def main():
             "gpu_launches_per_step": (N.launch_count() - l0) // (2 * args.steps) if False else None,
             "loss": float(loss), "optimizer": "AdamW(8e-4, wd 1e-2, betas (0.9,0.98), eps 1e-9), clip 0.5",
             "ddp": ("torch DDP over NCCL, static_graph" + (", fp16_compress_hook" if args.fp16_hook else "")) if world > 1 else "single process",
-            "dtype": "f32 (3x fp16 split-product tcgen05)", "data": "synthetic"}))
+            "dtype": ("%s operands, fp32 accumulate (single tcgen05 product)" % args.precision[:-2]) if args.precision.endswith("x1") else "f32 (3x %s split-product tcgen05)" % args.precision, "precision": args.precision, "data": "synthetic"}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
