@@ -51,8 +51,21 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class WgradDesc(ctypes.Structure):
+    """struct fd_wgrad_desc (include/fishdiff_b200.h)."""
+    _fields_ = [
+        ("row_src", c_void_p * 2), ("row_C", c_int * 2), ("col_src", c_void_p * 2), ("col_C", c_int * 2),
+        ("num_row_seg", c_int), ("row_seg_src", c_int * 2), ("row_seg_coff", c_int * 2), ("row_seg_width", c_int * 2),
+        ("num_col_seg", c_int), ("col_seg_src", c_int * 8), ("col_seg_shift", c_int * 8), ("col_seg_coff", c_int * 8),
+        ("col_seg_width", c_int * 8),
+        ("B", c_int), ("T", c_int), ("splits", c_int), ("part", c_void_p), ("acc_scale", c_float), ("prec", c_int),
+    ]
+
+
 _SIGS = {
     "fd_gemm_cl_fwd": (c_int, [POINTER(GemmDesc), c_void_p]),
+    "fd_wgrad_cl": (c_int, [POINTER(WgradDesc), c_void_p]),
+    "fd_colsum_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "fd_wavenet_block_fwd_train": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_void_p, c_float] +
                                    [c_int] * 6 + [c_float, c_float, c_int, c_int, c_int, c_void_p]),
     "fd_wavenet_gate_bias_from_d": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
@@ -275,3 +288,47 @@ def gemm_cl(src0, C0, w_planes, n_total, k_total, B, T, segs, *, src1=None, C1=0
     d.planes_scale, d.act_slope = planes_scale, act_slope
     d.out_accum, d.act, d.prec, d.backend = int(out_accum), act, prec, backend
     check(lib().fd_gemm_cl_fwd(ctypes.byref(d), stream_ptr(src0.device)), "fd_gemm_cl_fwd")
+
+
+def wgrad_supported(row_segs, col_segs) -> bool:
+    """Shapes the direct (MN-major tcgen05) weight-gradient kernel takes: every segment a multiple of 64 channels."""
+    return (1 <= len(row_segs) <= 2 and 1 <= len(col_segs) <= 8 and all(w % 64 == 0 and w > 0 for *_, w in row_segs)
+            and all(w % 64 == 0 and w > 0 for *_, w in col_segs))
+
+
+def wgrad_cl(row_srcs, col_srcs, row_segs, col_segs, B, T, *, scale=1.0, prec=PREC_F16, splits=None, out=None):
+    """sum_{b,t} ROW[b,t,r] * COL[b,t+shift,c] * scale -> fp32 [R, Cc]  (fd_wgrad_cl + fd_reduce_batch).
+    row_srcs / col_srcs: lists of 1..2 plane tensors [2,B,T,C]; row_segs = [(src, c_off, width)],
+    col_segs = [(src, shift, c_off, width)]."""
+    import torch
+    d = WgradDesc()
+    for i, t in enumerate(row_srcs):
+        assert t.dim() == 4 and t.shape[0] == 2 and t.shape[1] == B and t.shape[2] == T
+        d.row_src[i], d.row_C[i] = ptr(t), t.shape[3]
+    for i, t in enumerate(col_srcs):
+        assert t.dim() == 4 and t.shape[0] == 2 and t.shape[1] == B and t.shape[2] == T
+        d.col_src[i], d.col_C[i] = ptr(t), t.shape[3]
+    d.num_row_seg, d.num_col_seg = len(row_segs), len(col_segs)
+    R = Cc = 0
+    for j, (si, co, w) in enumerate(row_segs):
+        d.row_seg_src[j], d.row_seg_coff[j], d.row_seg_width[j] = si, co, w
+        R += w
+    for j, (si, sh, co, w) in enumerate(col_segs):
+        d.col_seg_src[j], d.col_seg_shift[j], d.col_seg_coff[j], d.col_seg_width[j] = si, sh, co, w
+        Cc += w
+    if splits is None:      # enough work units for ~2 waves of the 148 SMs, at most one partial per item
+        bn = 256 if Cc % 256 == 0 else 128 if Cc % 128 == 0 else 64
+        tiles = ((R + 127) // 128) * (Cc // bn)
+        splits = max(1, min(B, -(-296 // tiles)))
+    ips = -(-B // splits)
+    splits = -(-B // ips)
+    dev = row_srcs[0].device
+    part = torch.empty((splits, R, Cc), dtype=torch.float32, device=dev)
+    d.B, d.T, d.splits, d.part, d.acc_scale, d.prec = B, T, splits, ptr(part), 1.0, prec
+    st = stream_ptr(dev)
+    check(lib().fd_wgrad_cl(ctypes.byref(d), st), "fd_wgrad_cl")
+    if out is None:
+        out = torch.empty((R, Cc), dtype=torch.float32, device=dev)
+    assert tuple(out.shape) == (R, Cc) and out.dtype == torch.float32
+    check(lib().fd_reduce_batch(ptr(part), ptr(out), splits, R * Cc, float(scale), st), "fd_reduce_batch")
+    return out

@@ -121,6 +121,26 @@ __global__ void k_colsum(const uint16_t* __restrict__ planes, const float* __res
   atomicAdd(out + (size_t)b * N + n, acc * scale);
 }
 
+// column sums over the first / last `e` time steps of every item: out[edge][b][n] += scale * sum in[b,t,n],
+// edge 0: t in [0,e), edge 1: t in [T-e,T)   (conv-tap edge corrections of the step-vector term in the weight gradient)
+__global__ void k_colsum_edges(const uint16_t* __restrict__ planes, float* __restrict__ out, int B, int T, int N, int e,
+                               float scale, int rows_per_block, int chunks, int prec) {
+  const int b = blockIdx.z;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int edge = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+  const int base = edge == 0 ? 0 : T - e;
+  const int t0 = base + chunk * rows_per_block;
+  const int t1 = min(base + e, t0 + rows_per_block);
+  const size_t plane = (size_t)B * T * N;
+  float acc = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const size_t off = ((size_t)b * T + t) * N + n;
+    acc += fd_combine(planes[off], planes[plane + off], prec);
+  }
+  atomicAdd(out + ((size_t)edge * B + b) * N + n, acc * scale);
+}
+
 // out[i] = scale * sum_b in[b][i]
 __global__ void k_reduce_batch(const float* __restrict__ in, float* __restrict__ out, int B, long long n, float scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -184,6 +204,18 @@ int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T
   const int rows_per_block = 128;
   dim3 grid((N + 127) / 128, (T + rows_per_block - 1) / rows_per_block, B);
   k_colsum<<<grid, 128, 0, (cudaStream_t)stream>>>(planes, f32, out, B, T, N, scale, rows_per_block, prec);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_colsum_edges(const uint16_t* planes, float* out, int B, int T, int N, int e, float scale, int prec,
+                    void* stream) {
+  FD_REQUIRE(planes != nullptr && out != nullptr && e >= 0 && e <= T, "fd_colsum_edges: bad arguments (e=%d T=%d)", e, T);
+  if (e == 0) return 0;
+  const int rows_per_block = 64;
+  const int chunks = (e + rows_per_block - 1) / rows_per_block;
+  dim3 grid((N + 127) / 128, 2 * chunks, B);
+  k_colsum_edges<<<grid, 128, 0, (cudaStream_t)stream>>>(planes, out, B, T, N, e, scale, rows_per_block, chunks, prec);
   FD_LAUNCHED();
   return 0;
 }

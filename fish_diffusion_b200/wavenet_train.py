@@ -83,7 +83,7 @@ class WaveNetTrainFn(torch.autograd.Function):
                 "fd_wavenet_gate_bias_from_d")
         xs = torch.empty((L + 1, 2, B, T, C), **i16)      # residual stream entering each layer (x_L is unused)
         ys = torch.empty((L, 2, B, T, 2 * C), **i16)      # gate/filter pre-activations (packed order)
-        z = torch.empty((2, B, T, C), **i16)
+        zs = torch.empty((L, 2, B, T, C), **i16)          # gated activations (operand of the W2 weight gradient)
         skip_f32 = torch.empty((B, T, C), **f32)
         s_planes = torch.empty((2, B, T, C), **i16)
         h_planes = torch.empty((2, B, T, C), **i16)
@@ -94,7 +94,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         for l in range(L):
             flags = (1 if l == 0 else 0) | (2 if l == L - 1 else 0)
             N.check(lib.fd_wavenet_block_fwd_train(
-                N.ptr(xs[l]), N.ptr(xs[l + 1]), N.ptr(cond_planes), N.ptr(z), N.ptr(ys[l]), N.ptr(pk["w1"][l]),
+                N.ptr(xs[l]), N.ptr(xs[l + 1]), N.ptr(cond_planes), N.ptr(zs[l]), N.ptr(ys[l]), N.ptr(pk["w1"][l]),
                 N.ptr(pk["w2"][l]), N.ptr(gb[0, l]), N.ptr(gb[1, l]), N.ptr(gb[2, l]), gb_stride, N.ptr(pk["b2"][l]),
                 N.ptr(skip_f32), N.ptr(s_planes), 1.0 / math.sqrt(L), B, T, C, E, pk["dil"][l], pk["gate_tile"],
                 pk["w1_inv"][l], pk["w2_inv"][l], flags, mma, backend, st), "fd_wavenet_block_fwd_train")
@@ -103,7 +103,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         N.conv_cl(h_planes, pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], out_f32=eps, w_inv_scale=pk["w_out_inv"],
                   prec=mma, backend=backend)
         ctx.net = net
-        ctx.saved = dict(x_planes=x_planes, cond_planes=cond_planes, d=d, xs=xs, ys=ys, s_planes=s_planes,
+        ctx.saved = dict(x_planes=x_planes, cond_planes=cond_planes, d=d, xs=xs, ys=ys, zs=zs, s_planes=s_planes,
                          h_planes=h_planes, shape=(B, T, M, Bs))
         ctx.need_cond = cond_cl.requires_grad
         return eps
@@ -169,31 +169,50 @@ class WaveNetTrainFn(torch.autograd.Function):
             N.gemm_cl(src0, C0, w, n_total, k_total, B, T, segs, w_inv_scale=w_inv, prec=mma,
                       backend=_backend_for(pref, n_total, segs[0][3], len(segs)), **kw)
 
+        # Direct weight gradients (fd_wgrad_cl): the tensor core reads both operands MN-major straight from the
+        # channels-last planes, so no transposed copies exist on this path; the K-major fold path below it serves the
+        # SIMT back end and channel counts that are not multiples of 64.
+        direct = pref == N.BACKEND_TC and C % 64 == 0 and E % 64 == 0 and M % 64 == 0
+
+        def wgrad_direct(row_srcs, row_segs, col_srcs, col_segs, out=None):
+            return N.wgrad_cl(row_srcs, col_srcs, row_segs, col_segs, B, T, scale=inv_S, prec=mma, out=out)
+
         grads = {}
 
         # ---------------------------------------------------------------- tail (wavenet.py:229-231)
         de = d_eps.detach().to(torch.float32).contiguous()
         de_planes = N.split_nwc(de, prec, scale=S)
-        grads["output_projection.w"] = wgrad(fold(de_planes, M), M, fold(sv["h_planes"], C), C)       # [M, C]
+        if direct:
+            grads["output_projection.w"] = wgrad_direct([de_planes], [(0, 0, M)], [sv["h_planes"]], [(0, 0, 0, C)])
+        else:
+            grads["output_projection.w"] = wgrad(fold(de_planes, M), M, fold(sv["h_planes"], C), C)   # [M, C]
         grads["output_projection.b"] = colsum(f32t=de, Nn=M).sum(0)
         dh_raw = torch.empty((B, T, C), **f32)
         dgrad(de_planes, M, bw["wot"], bw["wot_inv"], C, M, [(0, 0, 0, M)], out_f32=dh_raw)
         dh_planes = torch.empty((2, B, T, C), **i16)
         N.check(lib.fd_relu_bwd(N.ptr(dh_raw), N.ptr(sv["h_planes"]), N.ptr(dh_planes), rows * C, 1.0, prec, st),
                 "fd_relu_bwd")
-        grads["skip_projection.w"] = wgrad(fold(dh_planes, C), C, fold(sv["s_planes"], C), C)
+        if direct:
+            grads["skip_projection.w"] = wgrad_direct([dh_planes], [(0, 0, C)], [sv["s_planes"]], [(0, 0, 0, C)])
+        else:
+            grads["skip_projection.w"] = wgrad(fold(dh_planes, C), C, fold(sv["s_planes"], C), C)
         grads["skip_projection.b"] = colsum(planes=dh_planes, Nn=C).sum(0)
         dskip_planes = torch.empty((2, B, T, C), **i16)                           # d(skip_l) = ds / sqrt(L), every layer
         dgrad(dh_planes, C, bw["wst"], bw["wst_inv"], C, C, [(0, 0, 0, C)], out_planes=dskip_planes,
               planes_scale=inv_sqrtL)
         cs_skip = colsum(planes=dskip_planes, Nn=C)                              # [B, C]
-        # stacked operands of the two weight-gradient GEMMs; the layer-invariant rows are written once
-        do_stack = torch.zeros((2, 2 * C, B, Tp), **i16)                         # [dx_next/sqrt2 ; d_skip]^T
-        fold(dskip_planes, C, dst=do_stack, row0=C)
-        xc_stack = torch.empty((2, KT, B, Tp), **i16)                            # [x(t-d)+d ; x(t)+d ; x(t+d)+d ; cond]^T
-        fold(sv["cond_planes"], E, dst=xc_stack, row0=3 * C)
-        dyT = torch.empty((2, 2 * C, B, Tp), **i16)
-        zT = torch.empty((2, C, B, Tp), **i16)
+        if direct:
+            cs_dy = torch.zeros((L, B, 2 * C), **f32)                            # column sums of dy per item
+            cs_edge = torch.zeros((L, 2, B, 2 * C), **f32)                       # ... over the first / last `dil` steps
+            gw2_all = torch.empty((L, 2 * C, C), **f32)
+        else:
+            # stacked operands of the two weight-gradient GEMMs; the layer-invariant rows are written once
+            do_stack = torch.zeros((2, 2 * C, B, Tp), **i16)                     # [dx_next/sqrt2 ; d_skip]^T
+            fold(dskip_planes, C, dst=do_stack, row0=C)
+            xc_stack = torch.empty((2, KT, B, Tp), **i16)                        # [x(t-d)+d ; x(t)+d ; x(t+d)+d ; cond]^T
+            fold(sv["cond_planes"], E, dst=xc_stack, row0=3 * C)
+            dyT = torch.empty((2, 2 * C, B, Tp), **i16)
+            zT = torch.empty((2, C, B, Tp), **i16)
         d_cond = torch.zeros((B, T, E), **f32) if ctx.need_cond else None
 
         # ---------------------------------------------------------------- residual blocks, last to first
@@ -216,22 +235,38 @@ class WaveNetTrainFn(torch.autograd.Function):
                           C1=C, out_f32=dz, w_inv_scale=bw["w2t_inv"][l], prec=mma,
                           backend=_backend_for(pref, C, C, 2))
             N.check(lib.fd_gate_bwd(N.ptr(dz), N.ptr(sv["ys"][l]), N.ptr(dy), rows, C, gate_tile, prec, st), "fd_gate_bwd")
-            # ---- weight gradient of the output projection: rows [residual | skip] x z
-            fold(sv["ys"][l], C, dst=zT, mode=1)
-            if dx_next is not None:
-                fold(dx_next, C, dst=do_stack, row0=0, scale=inv_sqrt2)
-            gw2 = wgrad(do_stack, 2 * C, zT, C)
             gb2 = torch.cat([cs_next.sum(0) * inv_sqrt2 if cs_next is not None else torch.zeros(C, **f32),
                              cs_skip.sum(0)])
-            grads[f"l{l}.w2"], grads[f"l{l}.b2"] = gw2, gb2
-            # ---- weight gradient of the dilated conv taps + conditioner projection in one GEMM (packed layout)
-            fold(dy, 2 * C, dst=dyT)
-            addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
-            for j, sh in enumerate((-dil, 0, dil)):
-                fold(sv["xs"][l], C, dst=xc_stack, row0=j * C, addvec=addvec, add_bstride=C if Bs > 1 else 0,
-                     pad=PAD - sh)
-            gw1_all[l] = wgrad(dyT, 2 * C, xc_stack, KT)
-            gb1_all[l] = colsum(planes=dy, Nn=2 * C).sum(0)
+            if direct:
+                # ---- rows [dx_next | d_skip] x z (the 1/sqrt2 of the residual rows is applied to all layers at the end)
+                if dx_next is not None:
+                    wgrad_direct([dx_next, dskip_planes], [(0, 0, C), (1, 0, C)], [sv["zs"][l]], [(0, 0, 0, C)],
+                                 out=gw2_all[l])
+                else:
+                    gw2_all[l, :C] = 0
+                    wgrad_direct([dskip_planes], [(0, 0, C)], [sv["zs"][l]], [(0, 0, 0, C)], out=gw2_all[l, C:])
+                grads[f"l{l}.b2"] = gb2
+                # ---- dy x [x(t-d) | x(t) | x(t+d) | cond]: taps are TMA row shifts of the same x planes; the step
+                #      vector d_l added to x inside the conv is a rank-one term, added for all layers after the loop
+                wgrad_direct([dy], [(0, 0, 2 * C)], [sv["xs"][l], sv["cond_planes"]],
+                             [(0, -dil, 0, C), (0, 0, 0, C), (0, dil, 0, C), (1, 0, 0, E)], out=gw1_all[l])
+                N.check(lib.fd_colsum(N.ptr(dy), None, N.ptr(cs_dy[l]), B, T, 2 * C, inv_S, prec, st), "fd_colsum")
+                N.check(lib.fd_colsum_edges(N.ptr(dy), N.ptr(cs_edge[l]), B, T, 2 * C, min(dil, T), inv_S, prec, st),
+                        "fd_colsum_edges")
+            else:
+                # ---- weight gradient of the output projection: rows [residual | skip] x z
+                fold(sv["ys"][l], C, dst=zT, mode=1)
+                if dx_next is not None:
+                    fold(dx_next, C, dst=do_stack, row0=0, scale=inv_sqrt2)
+                grads[f"l{l}.w2"], grads[f"l{l}.b2"] = wgrad(do_stack, 2 * C, zT, C), gb2
+                # ---- weight gradient of the dilated conv taps + conditioner projection in one GEMM (packed layout)
+                fold(dy, 2 * C, dst=dyT)
+                addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
+                for j, sh in enumerate((-dil, 0, dil)):
+                    fold(sv["xs"][l], C, dst=xc_stack, row0=j * C, addvec=addvec, add_bstride=C if Bs > 1 else 0,
+                         pad=PAD - sh)
+                gw1_all[l] = wgrad(dyT, 2 * C, xc_stack, KT)
+                gb1_all[l] = colsum(planes=dy, Nn=2 * C).sum(0)
             # ---- data gradients: dx_l = conv^T(dy) + dx_next/sqrt2 ;  dcond += dy . Wc
             dx_l = dx_bufs[l & 1]
             dgrad(dy, 2 * C, bw["w1t"][l], bw["w1t_inv"][l], C, 6 * C,
@@ -244,6 +279,20 @@ class WaveNetTrainFn(torch.autograd.Function):
             dd = cs_l if cs_next is None else cs_l - cs_next * inv_sqrt2               # d wrt the step vector d_l
             d_d[:, l, :] = dd if Bs > 1 else dd.sum(0, keepdim=True)
             dx_next, cs_next = dx_l, cs_l
+
+        if direct:
+            gb1_all = cs_dy.sum(1)
+            # conv input is x + d_l (zero padded): sum_t dy[t,r] * d[c] over the steps where tap j reads inside [0,T)
+            wj = torch.stack([cs_dy - cs_edge[:, 0], cs_dy, cs_dy - cs_edge[:, 1]], dim=1)        # [L,3,B,2C]
+            dl = sv["d"].transpose(0, 1)                                                            # [L,Bs,C]
+            if Bs > 1:
+                corr = torch.einsum("ljbr,lbc->lrjc", wj, dl)
+            else:
+                corr = torch.einsum("ljr,lc->lrjc", wj.sum(2), dl[:, 0])
+            gw1_all[:, :, :3 * C] += corr.reshape(L, 2 * C, 3 * C)
+            gw2_all[:, :C] *= inv_sqrt2
+            for l in range(L):
+                grads[f"l{l}.w2"] = gw2_all[l]
 
         # packed -> reference layouts for all layers at once
         gw1_o = torch.empty_like(gw1_all)
@@ -259,7 +308,10 @@ class WaveNetTrainFn(torch.autograd.Function):
         # dx_next now is d(x_0) where x_0 = relu(input_projection(x)): mask with x_0 > 0
         dx0m = torch.empty((2, B, T, C), **i16)
         N.check(lib.fd_relu_bwd(N.ptr(dx0), N.ptr(sv["xs"][0]), N.ptr(dx0m), rows * C, 1.0, prec, st), "fd_relu_bwd")
-        grads["input_projection.w"] = wgrad(fold(dx0m, C), C, fold(sv["x_planes"], M), M)
+        if direct:
+            grads["input_projection.w"] = wgrad_direct([dx0m], [(0, 0, C)], [sv["x_planes"]], [(0, 0, 0, M)])
+        else:
+            grads["input_projection.w"] = wgrad(fold(dx0m, C), C, fold(sv["x_planes"], M), M)
         grads["input_projection.b"] = colsum(planes=dx0m, Nn=C).sum(0)
 
         out = [None, None, d_cond, d_d]

@@ -229,6 +229,35 @@ int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_pla
  * out must be zero-initialised by the caller */
 int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T, int N, float scale, int prec,
               void* stream);
+/* out[edge][b][n] += scale * sum_t planes[b,t,n] over t in [0,e) (edge 0) and [T-e,T) (edge 1); out zero-initialised
+ * by the caller (edge terms of the step-vector contribution to the dilated-conv weight gradient) */
+int fd_colsum_edges(const uint16_t* planes, float* out, int B, int T, int N, int e, float scale, int prec,
+                    void* stream);
+
+/* Weight gradient straight from channels-last split planes, no transposes (tcgen05 with MN-major operands):
+ *   part[s][r][c] = acc_scale * sum_{b in split s} sum_t ROW[b,t,r] * COL[b,t+shift(c),c]
+ * Rows r are the concatenation of 1..2 row segments, columns c of 1..8 column segments; a segment names a source
+ * tensor (planes [2][B][T][C_src]), its first channel, its width (multiple of 64) and -- columns only -- a time shift
+ * (rows outside [0,T) read as zero: the conv zero padding of that tap).  Items are divided over `splits` partials
+ * (1 <= splits <= B; ceil(B/splits) consecutive items each) which the caller sums with fd_reduce_batch.
+ * Replaces autograd's conv-weight gradient of modules/wavenet.py:106-120 (reference runs it through cuDNN wgrad).
+ * `prec` may carry FD_PREC_SINGLE. */
+typedef struct fd_wgrad_desc {
+  const uint16_t* row_src[2];
+  int row_C[2];
+  const uint16_t* col_src[2];
+  int col_C[2];
+  int num_row_seg;
+  int row_seg_src[2], row_seg_coff[2], row_seg_width[2];
+  int num_col_seg;
+  int col_seg_src[8], col_seg_shift[8], col_seg_coff[8], col_seg_width[8];
+  int B, T, splits;
+  float* part;        /* [splits][R][Cc] fp32, R / Cc = total row / column widths */
+  float acc_scale;
+  int prec;
+} fd_wgrad_desc;
+int fd_wgrad_cl(const fd_wgrad_desc* d, void* stream);
+
 /* out[i] = scale * sum_b in[b][i]  (reduction of the per-item weight-gradient partials) */
 int fd_reduce_batch(const float* in, float* out, int B, long long n, float scale, void* stream);
 
