@@ -64,6 +64,7 @@ class WgradDesc(ctypes.Structure):
 
 _SIGS = {
     "fd_gemm_cl_fwd": (c_int, [POINTER(GemmDesc), c_void_p]),
+    "fd_wavenet_pack_layers": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fd_wgrad_cl": (c_int, [POINTER(WgradDesc), c_void_p]),
     "fd_colsum_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "fd_wavenet_block_fwd_train": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_void_p, c_float] +

@@ -76,6 +76,108 @@ __global__ void k_pack_weight(const float* __restrict__ w, uint16_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------- batched WaveNet weight packing
+// All residual layers in two launches, reading the raw parameters (conv [2C][C][3], conditioner [2C][E], output
+// projection [2C][C]) through device pointer tables: forward packs (gate/filter row interleave per column tile, taps
+// and conditioner concatenated along K), the fp32 copy the gate-bias fold reads, and -- for training -- the transposed
+// packs of the data-gradient GEMMs.  A training step repacks every step, so this replaces ~25 small launches per layer.
+struct PackLayersArgs {
+  const float* const* conv_w;
+  const float* const* cond_w;
+  const float* const* out_w;
+  const float* scales;      // [2][L]: s1 (conv + conditioner), s2 (output projection)
+  float* w1p_f32;           // [L][2C][KT]
+  uint16_t* w1;             // [L][2][2C][KT]
+  uint16_t* w2;             // [L][2][2C][C]
+  uint16_t* w1t;            // [L][2][C][6C]   or null
+  uint16_t* wct;            // [L][2][E][2C]   or null
+  uint16_t* w2t;            // [L][2][C][2C]   or null (residual half carries 1/sqrt2)
+  int L, C, E, half, prec;
+};
+
+__device__ __forceinline__ int packed_to_orig_row(int rp, int C, int half) {
+  const int q = rp / (2 * half), w = rp % (2 * half);
+  return w < half ? q * half + w : C + q * half + (w - half);
+}
+
+__global__ void k_pack_layers_w1(const PackLayersArgs a) {
+  __shared__ float tile[32][33];
+  const int l = blockIdx.z, C = a.C, E = a.E, KT = 3 * C + E, R = 2 * C;
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const float s1 = a.scales[l];
+  const float* cw = a.conv_w[l];
+  const float* dw = a.cond_w[l];
+  const size_t pl1 = (size_t)R * KT;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int rp = r0 + i, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (rp < R && k < KT) {
+      const int ro = packed_to_orig_row(rp, C, a.half);
+      v = k < 3 * C ? cw[((size_t)ro * C + (k % C)) * 3 + k / C] : dw[(size_t)ro * E + (k - 3 * C)];
+      a.w1p_f32[((size_t)l * R + rp) * KT + k] = v;
+      v *= s1;
+      uint16_t hi, lo;
+      fd_split(v, a.prec, hi, lo);
+      const size_t o = (size_t)l * 2 * pl1 + (size_t)rp * KT + k;
+      a.w1[o] = hi;
+      a.w1[o + pl1] = lo;
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (a.w1t == nullptr) return;
+  __syncthreads();
+  const size_t plt = (size_t)C * 6 * C, plc = (size_t)E * R;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, rp = r0 + threadIdx.x;
+    if (rp >= R || k >= KT) continue;
+    uint16_t hi, lo;
+    fd_split(tile[threadIdx.x][i], a.prec, hi, lo);
+    if (k < 3 * C) {
+      const int j = k / C, c = k % C;
+      const size_t o = (size_t)l * 2 * plt + (size_t)c * 6 * C + (size_t)j * R + rp;
+      a.w1t[o] = hi;
+      a.w1t[o + plt] = lo;
+    } else {
+      const size_t o = (size_t)l * 2 * plc + (size_t)(k - 3 * C) * R + rp;
+      a.wct[o] = hi;
+      a.wct[o + plc] = lo;
+    }
+  }
+}
+
+__global__ void k_pack_layers_w2(const PackLayersArgs a) {
+  __shared__ float tile[32][33];
+  const int l = blockIdx.z, C = a.C, R = 2 * C;
+  const int n0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float s2 = a.scales[a.L + l];
+  const float* ow = a.out_w[l];
+  const size_t pl = (size_t)R * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (n < R && c < C) {
+      v = ow[(size_t)n * C + c] * s2;
+      uint16_t hi, lo;
+      fd_split(v, a.prec, hi, lo);
+      const size_t o = (size_t)l * 2 * pl + (size_t)n * C + c;
+      a.w2[o] = hi;
+      a.w2[o + pl] = lo;
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (a.w2t == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, n = n0 + threadIdx.x;
+    if (n >= R || c >= C) continue;
+    uint16_t hi, lo;
+    fd_split(tile[threadIdx.x][i] * (n < C ? 0.70710678118654752440f : 1.f), a.prec, hi, lo);
+    const size_t o = (size_t)l * 2 * pl + (size_t)c * R + n;
+    a.w2t[o] = hi;
+    a.w2t[o + pl] = lo;
+  }
+}
+
 // ---------------------------------------------------------------------------------- step embedding
 // wavenet.py:20-27: emb_j = exp(j * -(ln(1e4)/(half-1))) ; [sin(t*emb), cos(t*emb)]
 __global__ void k_step_embed(const float* __restrict__ steps, float* __restrict__ emb, int Bs, int C) {
@@ -292,6 +394,23 @@ int fd_transpose_ncw_to_nwc(const float* src, float* dst, int B, int C, int T, v
 
 int fd_pack_weight(const float* w, uint16_t* planes, long long n_elems, float scale, int prec, void* stream) {
   k_pack_weight<<<grid_for(n_elems), 256, 0, (cudaStream_t)stream>>>(w, planes, n_elems, scale, prec);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_wavenet_pack_layers(const float* const* conv_w, const float* const* cond_w, const float* const* out_w,
+                           const float* scales, float* w1p_f32, uint16_t* w1, uint16_t* w2, uint16_t* w1t, uint16_t* wct,
+                           uint16_t* w2t, int L, int C, int E, int gate_half, int prec, void* stream) {
+  FD_REQUIRE(L > 0 && C > 0 && E > 0 && gate_half > 0 && C % gate_half == 0, "fd_wavenet_pack_layers: bad shape");
+  FD_REQUIRE(conv_w && cond_w && out_w && scales && w1p_f32 && w1 && w2, "fd_wavenet_pack_layers: null pointer");
+  FD_REQUIRE((w1t == nullptr) == (wct == nullptr) && (w1t == nullptr) == (w2t == nullptr),
+             "fd_wavenet_pack_layers: the transposed packs come all or none");
+  PackLayersArgs a{conv_w, cond_w, out_w, scales, w1p_f32, w1, w2, w1t, wct, w2t, L, C, E, gate_half, prec};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KT = 3 * C + E;
+  k_pack_layers_w1<<<dim3((KT + 31) / 32, (2 * C + 31) / 32, L), dim3(32, 8), 0, st>>>(a);
+  FD_LAUNCHED();
+  k_pack_layers_w2<<<dim3((C + 31) / 32, (2 * C + 31) / 32, L), dim3(32, 8), 0, st>>>(a);
   FD_LAUNCHED();
   return 0;
 }

@@ -39,7 +39,10 @@ class DenoiserTrainer:
             self.ddp = DDP(self.module, device_ids=dev_ids, gradient_as_bucket_view=True, static_graph=True)
             if fp16_compress:
                 self.ddp.register_comm_hook(None, default_hooks.fp16_compress_hook)
-        self.opt = torch.optim.AdamW(diffusion.parameters(), lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
+        params = list(diffusion.parameters())
+        # same update rule as the reference's torch.optim.AdamW; the fused (single multi-tensor kernel) implementation
+        fused = all(p.is_cuda for p in params)
+        self.opt = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps, fused=fused)
         self.clip = clip
 
     def step(self, features, mel, t=None, noise=None):

@@ -112,6 +112,9 @@ class WaveNet(nn.Module):
         self.backend = os.environ.get("FD_BACKEND", backend)
         self._pack = None
         self._pack_key = None
+        self._pack_static = None
+        self._scale_state = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_scale_state", None))
         self._ws = {}
 
     # ------------------------------------------------------------------------------------ packing
@@ -122,72 +125,127 @@ class WaveNet(nn.Module):
         ok = (C % 64 == 0 and E % 64 == 0 and M % 64 == 0 and _gate_half(C) in (128, 64))
         return N.BACKEND_TC if ok else N.BACKEND_SIMT
 
-    def _packed(self, device):
-        key = (str(device), self.precision, tuple(p._version for p in self.parameters()),
-               tuple(p.data_ptr() for p in self.parameters()))
-        if self._pack is not None and self._pack_key == key:
-            return self._pack
-        prec = N.prec_code(self.precision)
-        C, E, M, L = self.residual_channels, self.d_encoder, self.mel_channels, self.n_layers
-        half = _gate_half(C)
-        gate_tile = 2 * half
-        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32)
-        # gate/filter row interleave per column tile: tile q holds gates [q*half,(q+1)*half) then their filters
-        idx = torch.arange(C, device=device).view(C // half, half)
-        perm = torch.cat([idx, idx + C], dim=1).reshape(-1)
-
-        # power-of-two prescales of every packed matrix from ONE device->host transfer (training repacks every step)
+    def _scales(self, device, lag_ok=False):
+        """Power-of-two prescales of every packed matrix (max |w| * s in [32, 64)); they need max |w| on the host.
+        Inference repacks are rare and read it synchronously.  A training loop repacks every step: there (`lag_ok`) the
+        maxima are fetched asynchronously into pinned memory and consumed by the NEXT repack, so no step waits for a
+        device->host round trip; the one-step lag is harmless (fp16 planes saturate at 65504 = 2^10 above the target
+        range) and load_state_dict() drops the lagged values."""
+        L = self.n_layers
         raw = [self.input_projection.conv.weight, self.skip_projection.conv.weight, self.output_projection.conv.weight]
         for blk in self.residual_layers:
             raw += [blk.conv_layer.conv.weight, blk.conditioner_projection.conv.weight, blk.output_projection.conv.weight]
-        amax = torch.stack(torch._foreach_norm([w.detach() for w in raw], float("inf"))).tolist()
+
+        def amax_dev():
+            return torch.stack(torch._foreach_norm([w.detach() for w in raw], float("inf"))).to(torch.float32)
+
+        st = self._scale_state
+        pending = st.get("pending") if (lag_ok and st is not None and st["device"] == str(device)) else None
+        if pending is not None:
+            pending[0].synchronize()
+            amax = pending[1].tolist()
+        else:
+            amax = amax_dev().tolist()
 
         def p2(m):
             return 1.0 if m == 0.0 or m != m else float(2.0 ** math.floor(math.log2(64.0 / m)))
 
-        s_in, s_skip, s_out = p2(amax[0]), p2(amax[1]), p2(amax[2])
         s1 = [p2(max(amax[3 + 3 * l], amax[4 + 3 * l])) for l in range(L)]
         s2 = [p2(amax[5 + 3 * l]) for l in range(L)]
+        new = {"device": str(device), "s_in": p2(amax[0]), "s_skip": p2(amax[1]), "s_out": p2(amax[2]), "s1": s1, "s2": s2}
+        if st is not None and st["device"] == str(device) and st["s1"] == s1 and st["s2"] == s2:
+            new["dev"] = st["dev"]
+        else:
+            new["dev"] = torch.tensor(s1 + s2, dtype=torch.float32, device=device)
+        if lag_ok and device.type == "cuda":
+            host = st["pending"][1] if pending is not None else torch.empty(len(raw), dtype=torch.float32).pin_memory()
+            host.copy_(amax_dev(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            new["pending"] = (ev, host)
+        self._scale_state = new
+        return new
 
-        def pack(w2d, sc):
-            return N.pack_weight(w2d, prec, sc), 1.0 / sc
+    def _packed(self, device, want_bwd=False):
+        """Packed weights for `device`, rebuilt whenever a parameter changed (version counters).  All residual layers
+        are packed by ONE batched native call (fd_wavenet_pack_layers) that reads the parameters in place; with
+        `want_bwd` the transposed packs of the data-gradient GEMMs are produced by the same launches."""
+        key = (str(device), self.precision, tuple(p._version for p in self.parameters()),
+               tuple(p.data_ptr() for p in self.parameters()))
+        if self._pack is not None and self._pack_key == key and (self._pack["has_bwd"] or not want_bwd):
+            return self._pack
+        prec = N.prec_code(self.precision)
+        C, E, M, L = self.residual_channels, self.d_encoder, self.mel_channels, self.n_layers
+        KT = 3 * C + E
+        half = _gate_half(C)
+        gate_tile = 2 * half
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32)
+        sc = self._scales(device, lag_ok=want_bwd)
+        s_in, s_skip, s_out, s1, s2 = sc["s_in"], sc["s_skip"], sc["s_out"], sc["s1"], sc["s2"]
 
-        pk = {"prec": prec, "mma": N.mma_code(self.precision), "gate_tile": gate_tile, "backend": self._resolve_backend(), "perm": perm,
-              "s_in": s_in, "s_skip": s_skip, "s_out": s_out, "s1": s1, "s2": s2}
+        # persistent buffers + parameter pointer tables (rebuilt only when a parameter moved)
+        stat = self._pack_static
+        has_bwd = bool(want_bwd or (stat is not None and stat["has_bwd"]))
+        ptr_key = (str(device), self.precision, has_bwd)
+        if stat is None or stat["key"] != ptr_key:
+            i16 = dict(dtype=torch.int16, device=device)
+            idx = torch.arange(C, device=device).view(C // half, half)
+            stat = {"key": ptr_key, "has_bwd": has_bwd,
+                    # gate/filter row interleave per column tile: tile q holds gates [q*half,(q+1)*half) then filters
+                    "perm": torch.cat([idx, idx + C], dim=1).reshape(-1),
+                    "w1p_f32": torch.empty((L, 2 * C, KT), dtype=torch.float32, device=device),
+                    "w1": torch.empty((L, 2, 2 * C, KT), **i16), "w2": torch.empty((L, 2, 2 * C, C), **i16),
+                    "w1t": torch.empty((L, 2, C, 6 * C), **i16) if has_bwd else None,
+                    "wct": torch.empty((L, 2, E, 2 * C), **i16) if has_bwd else None,
+                    "w2t": torch.empty((L, 2, C, 2 * C), **i16) if has_bwd else None}
+            self._pack_static = stat
+        srcs = [[f32(b.conv_layer.conv.weight).contiguous() for b in self.residual_layers],
+                [f32(b.conditioner_projection.conv.weight).contiguous() for b in self.residual_layers],
+                [f32(b.output_projection.conv.weight).contiguous() for b in self.residual_layers]]
+        src_ptrs = tuple(t.data_ptr() for grp in srcs for t in grp)
+        if stat.get("src_ptrs") != src_ptrs:
+            stat["src_ptrs"] = src_ptrs
+            stat["ptr_table"] = torch.tensor(src_ptrs, dtype=torch.int64).view(3, L).to(device)
+        tab = stat["ptr_table"]
+        N.check(N.lib().fd_wavenet_pack_layers(
+            N.ptr(tab[0]), N.ptr(tab[1]), N.ptr(tab[2]), N.ptr(sc["dev"]), N.ptr(stat["w1p_f32"]), N.ptr(stat["w1"]),
+            N.ptr(stat["w2"]), N.ptr(stat["w1t"]), N.ptr(stat["wct"]), N.ptr(stat["w2t"]), L, C, E, half, prec,
+            N.stream_ptr(device)), "fd_wavenet_pack_layers")
+
+        def pack(w2d, scale):
+            return N.pack_weight(w2d, prec, scale), 1.0 / scale
+
+        pk = {"prec": prec, "mma": N.mma_code(self.precision), "gate_tile": gate_tile,
+              "backend": self._resolve_backend(), "perm": stat["perm"], "has_bwd": stat["has_bwd"],
+              "s_in": s_in, "s_skip": s_skip, "s_out": s_out, "s1": s1, "s2": s2, "_srcs": srcs}
         pk["w_in"], pk["w_in_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0], s_in)
         pk["b_in"] = f32(self.input_projection.conv.bias).contiguous()
         pk["mlp_w0"] = f32(self.mlp[0].linear.weight).contiguous()
         pk["mlp_b0"] = f32(self.mlp[0].linear.bias).contiguous() if self.mlp[0].linear.bias is not None else None
         pk["mlp_w1"] = f32(self.mlp[2].linear.weight).contiguous()
         pk["mlp_b1"] = f32(self.mlp[2].linear.bias).contiguous() if self.mlp[2].linear.bias is not None else None
-        w1p, bsum, w1pl, w1inv, w2pl, w2inv, b2, wd, bd, dil = [], [], [], [], [], [], [], [], [], []
-        for li, blk in enumerate(self.residual_layers):
-            wc = f32(blk.conv_layer.conv.weight)                     # [2C, C, 3]
-            wcond = f32(blk.conditioner_projection.conv.weight)[:, :, 0]   # [2C, E]
-            w1 = torch.cat([wc[:, :, 0], wc[:, :, 1], wc[:, :, 2], wcond], dim=1)[perm].contiguous()  # [2C, 3C+E]
-            w1p.append(w1)
-            bsum.append((f32(blk.conv_layer.conv.bias) + f32(blk.conditioner_projection.conv.bias))[perm])
-            pl1, i1 = pack(w1, s1[li])
-            w1pl.append(pl1); w1inv.append(i1)
-            pl2, i2 = pack(f32(blk.output_projection.conv.weight)[:, :, 0], s2[li])
-            w2pl.append(pl2); w2inv.append(i2)
-            b2.append(f32(blk.output_projection.conv.bias))
-            wd.append(f32(blk.diffusion_projection.linear.weight))
-            if blk.diffusion_projection.linear.bias is not None:
-                bd.append(f32(blk.diffusion_projection.linear.bias))
-            dil.append(blk.dilation)
-        pk["w1p_f32"] = torch.stack(w1p).contiguous()
-        pk["bias_sum"] = torch.stack(bsum).contiguous()
-        pk["w1"], pk["w1_inv"] = w1pl, w1inv
-        pk["w2"], pk["w2_inv"] = w2pl, w2inv
-        pk["b2"] = torch.stack(b2).contiguous()
-        pk["wd"] = torch.stack(wd).contiguous()
-        pk["bd"] = torch.stack(bd).contiguous() if bd else None
-        pk["dil"] = dil
+        blocks = list(self.residual_layers)
+        pk["w1p_f32"] = stat["w1p_f32"]
+        pk["bias_sum"] = (torch.stack([f32(b.conv_layer.conv.bias) for b in blocks]) +
+                          torch.stack([f32(b.conditioner_projection.conv.bias) for b in blocks]))[:, stat["perm"]].contiguous()
+        pk["w1"], pk["w1_inv"] = [stat["w1"][l] for l in range(L)], [1.0 / v for v in s1]
+        pk["w2"], pk["w2_inv"] = [stat["w2"][l] for l in range(L)], [1.0 / v for v in s2]
+        pk["b2"] = torch.stack([f32(b.output_projection.conv.bias) for b in blocks]).contiguous()
+        pk["wd"] = torch.stack([f32(b.diffusion_projection.linear.weight) for b in blocks]).contiguous()
+        pk["bd"] = (torch.stack([f32(b.diffusion_projection.linear.bias) for b in blocks]).contiguous()
+                    if blocks[0].diffusion_projection.linear.bias is not None else None)
+        pk["dil"] = [b.dilation for b in blocks]
         pk["w_skip"], pk["w_skip_inv"] = pack(f32(self.skip_projection.conv.weight)[:, :, 0], s_skip)
         pk["b_skip"] = f32(self.skip_projection.conv.bias).contiguous()
         pk["w_out"], pk["w_out_inv"] = pack(f32(self.output_projection.conv.weight)[:, :, 0], s_out)
         pk["b_out"] = f32(self.output_projection.conv.bias).contiguous()
+        if stat["has_bwd"]:
+            bw = {"w1t": [stat["w1t"][l] for l in range(L)], "w1t_inv": pk["w1_inv"],
+                  "wct": [stat["wct"][l] for l in range(L)], "wct_inv": pk["w1_inv"],
+                  "w2t": [stat["w2t"][l] for l in range(L)], "w2t_inv": pk["w2_inv"]}
+            bw["wot"], bw["wot_inv"] = pack(f32(self.output_projection.conv.weight)[:, :, 0].t().contiguous(), s_out)
+            bw["wst"], bw["wst_inv"] = pack(f32(self.skip_projection.conv.weight)[:, :, 0].t().contiguous(), s_skip)
+            pk["_bwd"] = bw
         self._pack, self._pack_key = pk, key
         return pk
 

@@ -31,31 +31,11 @@ def _backend_for(pref, n_total, k_seg, num_seg):
 
 
 def _bwd_packs(net, pk, device):
-    """Transposed packed weights of the data-gradient GEMMs for all layers, built with a few batched tensor ops per
-    optimisation step (cached next to the forward packs; power-of-two prescales reused from them: no host sync)."""
-    if pk.get("_bwd") is not None:
-        return pk["_bwd"]
-    prec = pk["prec"]
-    C, L = net.residual_channels, net.n_layers
-    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32)
-    W1 = pk["w1p_f32"]                                                   # [L, 2C, 3C+E] packed row order
-    W1T = W1[:, :, :3 * C].reshape(L, 2 * C, 3, C).permute(0, 3, 2, 1).reshape(L, C, 6 * C).contiguous()
-    WcT = W1[:, :, 3 * C:].transpose(1, 2).contiguous()                  # [L, E, 2C]
-    W2 = torch.stack([f32(b.output_projection.conv.weight)[:, :, 0] for b in net.residual_layers])   # [L, 2C, C]
-    W2T = W2.transpose(1, 2).contiguous()                                # [L, C, 2C]
-    W2T[:, :, :C] *= 1.0 / math.sqrt(2.0)                                # residual half carries the 1/sqrt2
-    bw = {"w1t": [], "w1t_inv": [], "wct": [], "wct_inv": [], "w2t": [], "w2t_inv": []}
-    for l in range(L):
-        s1, s2 = pk["s1"][l], pk["s2"][l]
-        bw["w1t"].append(N.pack_weight(W1T[l], prec, s1)); bw["w1t_inv"].append(1.0 / s1)
-        bw["wct"].append(N.pack_weight(WcT[l], prec, s1)); bw["wct_inv"].append(1.0 / s1)
-        bw["w2t"].append(N.pack_weight(W2T[l], prec, s2)); bw["w2t_inv"].append(1.0 / s2)
-    bw["wot"] = N.pack_weight(f32(net.output_projection.conv.weight)[:, :, 0].t().contiguous(), prec, pk["s_out"])
-    bw["wot_inv"] = 1.0 / pk["s_out"]
-    bw["wst"] = N.pack_weight(f32(net.skip_projection.conv.weight)[:, :, 0].t().contiguous(), prec, pk["s_skip"])
-    bw["wst_inv"] = 1.0 / pk["s_skip"]
-    pk["_bwd"] = bw
-    return bw
+    """Transposed packed weights of the data-gradient GEMMs (made by the same batched pack launches as the forward
+    packs when the forward ran with gradients enabled; see WaveNet._packed)."""
+    if pk.get("_bwd") is None:
+        pk = net._packed(device, want_bwd=True)
+    return pk["_bwd"]
 
 
 class WaveNetTrainFn(torch.autograd.Function):
@@ -68,7 +48,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         B, T, M = x_cl.shape
         C, E, L = net.residual_channels, net.d_encoder, net.n_layers
         Bs = d.shape[0]
-        pk = net._packed(dev)                       # forward packs (re-made whenever a parameter version changes)
+        pk = net._packed(dev, want_bwd=True)        # packs are re-made whenever a parameter version changes
         prec, mma, backend = pk["prec"], pk["mma"], pk["backend"]
         lib, st = N.lib(), N.stream_ptr(dev)
         i16 = dict(dtype=torch.int16, device=dev)
@@ -114,7 +94,7 @@ class WaveNetTrainFn(torch.autograd.Function):
         B, T, M, Bs = sv["shape"]
         C, E, L = net.residual_channels, net.d_encoder, net.n_layers
         dev = d_eps.device
-        pk = net._packed(dev)
+        pk = net._packed(dev, want_bwd=True)
         bw = _bwd_packs(net, pk, dev)
         prec, mma, pref = pk["prec"], pk["mma"], pk["backend"]
         perm, gate_tile = pk["perm"], pk["gate_tile"]

@@ -62,6 +62,16 @@ int fd_transpose_ncw_to_nwc(const float* src, float* dst, int B, int C, int T, v
 /* fp32 weight matrix [N][K] -> split planes [2][N][K] of (w*scale) */
 int fd_pack_weight(const float* w, uint16_t* planes, long long n_elems, float scale, int prec, void* stream);
 
+/* All residual layers of a WaveNet packed in two launches from the raw parameters (device pointer tables of L entries:
+ * conv weight [2C][C][3], conditioner weight [2C][E], output-projection weight [2C][C]; modules/wavenet.py:88-104).
+ *   w1p_f32 [L][2C][3C+E]   fp32, rows in gate/filter-interleaved order (tile = 2*gate_half), K = tap0|tap1|tap2|cond
+ *   w1 [L][2][2C][3C+E], w2 [L][2][2C][C]                     forward packs, scaled by scales[l] / scales[L+l]
+ *   w1t [L][2][C][6C], wct [L][2][E][2C], w2t [L][2][C][2C]   transposed packs of the data-gradient GEMMs (all three or
+ *                                                             all NULL); the residual half of w2t carries 1/sqrt2 */
+int fd_wavenet_pack_layers(const float* const* conv_w, const float* const* cond_w, const float* const* out_w,
+                           const float* scales, float* w1p_f32, uint16_t* w1, uint16_t* w2, uint16_t* w1t, uint16_t* wct,
+                           uint16_t* w2t, int L, int C, int E, int gate_half, int prec, void* stream);
+
 /* ------------------------------------------------------------------------- WaveNet denoiser (a10-a12) */
 /* DiffusionEmbedding + mlp (wavenet.py:13-27,170-174,214-215): steps[Bs] (float; int steps are cast by
  * the caller exactly like `x[:, None] * emb`) -> s[Bs][C].
