@@ -20,8 +20,6 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 256;                       // 8 epilogue warps
-constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;
 
 // NPL = operand planes staged per k-block: 2 (hi + lo, three products) or 1 (hi only, one product: 11-bit (f16) /
 // 8-bit (bf16) operand mantissas, the arithmetic of a plain half-precision tensor-core GEMM with fp32 accumulation).
@@ -36,15 +34,18 @@ struct Cfg {
   static constexpr int SUB_BYTES = NPL * (A_BYTES + W_BYTES);           // multiple of 1024 for every instantiation
   static constexpr int STAGE_BYTES = GROUP * SUB_BYTES;
   static constexpr int TX_BYTES = SUB_BYTES;                            // per k-block
-  static constexpr int RAW_STAGES = (200 * 1024) / STAGE_BYTES;
-  static constexpr int NUM_STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   // BLOCK_N = 256: the two epilogue warps of a TMEM lane quadrant split the columns of one tile (2 accumulator
   // stages fill the 512 TMEM columns).  Narrower tiles: the two groups of 4 epilogue warps take ALTERNATE tiles and
   // 4 accumulator stages keep the MMA warp ahead -- the per-tile epilogue latency chain (bias, TMEM load, global
   // read-modify-write) of one group overlaps the other group's.
+  // The epilogue of such tiles is bound by the latency of its global operands, i.e. by how many tiles are in flight per
+  // SM: tiles of <= 32 columns (small per-thread state) run FOUR groups of 4 warps, one accumulator stage each; 64 / 128
+  // columns keep two groups (the coalescing epilogue needs more than the 96 registers a 640-thread CTA leaves).
   static constexpr bool SPLIT_COLS = BLOCK_N >= 256;
   static constexpr int ACC_STAGES = SPLIT_COLS ? 2 : 4;
-  static constexpr int EPI_GROUPS = SPLIT_COLS ? 1 : 2;
+  static constexpr int EPI_GROUPS = SPLIT_COLS ? 1 : (BLOCK_N <= 32 ? 4 : 2);
+  static constexpr int EPI_THREADS = SPLIT_COLS ? 256 : 128 * EPI_GROUPS;
+  static constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BLOCK_N;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
@@ -55,12 +56,16 @@ struct Cfg {
   // coalescing epilogue (LINEAR / RES_SKIP with >= 32 columns per warp): a 32x32 fp32 transpose scratch per warp
   static constexpr bool COALESCED = (EPI == FD_EPI_LINEAR || EPI == FD_EPI_RES_SKIP) && BLOCK_N >= 64;
   static constexpr int SCRATCH_BYTES = COALESCED ? (EPI_THREADS / 32) * 4096 : 0;
+  static constexpr int FIXED_BYTES = 1024 /*align slack*/ + BIAS_FLOATS * 4 + (2 * 8 + 2 * ACC_STAGES) * 8 + 16 + SCRATCH_BYTES;
+  static constexpr int RAW_STAGES = (227 * 1024 - 512 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int NUM_STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + BIAS_FLOATS * 4 +
                                     (2 * NUM_STAGES + 2 * ACC_STAGES) * 8 + 16 + SCRATCH_BYTES;
+  static_assert(NUM_STAGES >= 2, "pipeline needs at least two stages");
 };
 
 template <int BLOCK_N, int BLOCK_K, int EPI, int PREC, int NPL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Cfg<BLOCK_N, BLOCK_K, EPI, NPL>::NUM_THREADS), 1)
 fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                      const __grid_constant__ CUtensorMap tm_w, const FdTapGemm p) {
   using C = Cfg<BLOCK_N, BLOCK_K, EPI, NPL>;
@@ -92,7 +97,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::NUM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_THREADS / 32 / C::EPI_GROUPS); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], C::EPI_THREADS / 32 / C::EPI_GROUPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -183,18 +188,19 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
     // =========================================================== epilogue (8 warps)
     // warp w may access TMEM lanes [32*(w%4), +32); the two warps of a lane quadrant split the columns.
     const int q = warp % 4;
-    const int wgrp = (warp - EPI_WARP0) / 4;                 // 0 / 1: which set of four epilogue warps
+    const int wgrp = (warp - EPI_WARP0) / 4;                 // which set of four epilogue warps
     const int half = C::SPLIT_COLS ? wgrp : 0;               // column half handled inside a shared tile
     const int group = C::SPLIT_COLS ? 0 : wgrp;              // alternate-tile group
-    constexpr int GTHREADS = EPI_THREADS / C::EPI_GROUPS;    // threads cooperating on one tile
+    constexpr int GTHREADS = C::EPI_THREADS / C::EPI_GROUPS; // threads cooperating on one tile
     const int row = q * 32 + lane;
     const int etid = (threadIdx.x - EPI_WARP0 * 32) % GTHREADS;
     constexpr int HALVES = C::SPLIT_COLS ? 2 : 1;
     float* const bias_g = bias_s + group * (C::BIAS_FLOATS / C::EPI_GROUPS);
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
+    long long staged_key = -1;                               // which bias vectors this group holds in shared memory
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      if (C::EPI_GROUPS == 2 && (it & 1) != group) {         // the other group's tile: just keep the stage counters
+      if (C::EPI_GROUPS > 1 && (it % C::EPI_GROUPS) != group) {   // another group's tile: just keep the stage counters
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         continue;
       }
@@ -207,22 +213,27 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
       const int t = t0 + row;
       const bool valid = t < p.T;
 
-      // stage the per-column bias vectors of this tile in shared memory (named barrier of this tile's warps)
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
-      if (EPI == FD_EPI_MAG) {
-        // no bias
-      } else if (EPI == FD_EPI_GATE) {
-        const size_t bo = (size_t)b * p.gbias_bstride + n0;
-        for (int i = etid; i < BLOCK_N; i += GTHREADS) {
-          bias_g[i] = p.gbias_full[bo + i];
-          bias_g[BLOCK_N + i] = p.gbias_lo[bo + i];
-          bias_g[2 * BLOCK_N + i] = p.gbias_hi[bo + i];
+      // stage the per-column bias vectors of this tile in shared memory (named barrier of this tile's warps); skipped
+      // while the group keeps seeing the same columns / item -- with a single column tile that is once per launch, which
+      // takes a dependent global load and two barriers out of every tile's latency chain
+      const long long bias_key = EPI == FD_EPI_GATE ? (long long)b * p.gbias_bstride + n0
+                                                    : (long long)b * p.bias_bstride + n0;
+      if (EPI != FD_EPI_MAG && bias_key != staged_key) {
+        staged_key = bias_key;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
+        if (EPI == FD_EPI_GATE) {
+          const size_t bo = (size_t)b * p.gbias_bstride + n0;
+          for (int i = etid; i < BLOCK_N; i += GTHREADS) {
+            bias_g[i] = p.gbias_full[bo + i];
+            bias_g[BLOCK_N + i] = p.gbias_lo[bo + i];
+            bias_g[2 * BLOCK_N + i] = p.gbias_hi[bo + i];
+          }
+        } else {
+          for (int i = etid; i < BLOCK_N; i += GTHREADS)
+            bias_g[i] = p.bias ? p.bias[(size_t)b * p.bias_bstride + n0 + i] : 0.f;
         }
-      } else {
-        for (int i = etid; i < BLOCK_N; i += GTHREADS)
-          bias_g[i] = p.bias ? p.bias[(size_t)b * p.bias_bstride + n0 + i] : 0.f;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -264,12 +275,16 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
         const uint32_t bias_addr = smem_u32(bias_g);
         const int j4 = (lane & 7) * 4, rsub = lane >> 3;
         const int rbase = t0 + q * 32 + rsub;            // time index of pass 0
+#pragma unroll 1
         for (int c = 0; c < PER; c += 32) {
           const int col = half * PER + c + j4;           // first of this lane's 4 columns inside the tile
           const int n = n0 + col;                        // global packed column
           float v[32];
-          tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
-          tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+          constexpr bool LATE_TMEM_LD = EPI == FD_EPI_LINEAR && !C::SPLIT_COLS;   // see the LINEAR branch below
+          if (!LATE_TMEM_LD) {
+            tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+          }
           const float4 bias4 = lds128(bias_addr + 4u * col);
           if (EPI == FD_EPI_RES_SKIP) {
             const bool is_res = n0 < p.C;
@@ -326,6 +341,101 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 } else {
                   *reinterpret_cast<float4*>(p.skip_f32 + ro + (n - p.C)) = make_float4(y[0], y[1], y[2], y[3]);
                 }
+              }
+            }
+          } else if (!C::SPLIT_COLS) {
+            // LINEAR, 64 / 128-column tiles (vocoder convs): this epilogue is bound by the latency of its global
+            // operands, so ALL of a chunk's operand loads (8 rows x 16 bytes per lane and operand kind) are issued up
+            // front -- before the TMEM load and the transposes -- and folded kind by kind into one pre-sum, which keeps
+            // the register cost at one kind in flight regardless of how many kinds a launch uses.
+            const size_t plane = (size_t)p.B * p.T * p.n_total;
+            const size_t off0 = ((size_t)b * p.T + rbase) * p.n_total + n;     // row pp of this lane: + pp * rstep
+            const size_t rstep = (size_t)4 * p.n_total;
+            const int nrows = rbase < p.T ? min(8, (p.T - rbase + 3) / 4) : 0;  // rows rbase + 4*pp < T
+            float4 pre[8];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) pre[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.addend != nullptr) {
+              float4 t4[8];
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp) if (pp < nrows) t4[pp] = *reinterpret_cast<const float4*>(p.addend + off0 + pp * rstep);
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp)
+                if (pp < nrows) { pre[pp].x += t4[pp].x; pre[pp].y += t4[pp].y; pre[pp].z += t4[pp].z; pre[pp].w += t4[pp].w; }
+            }
+            asm volatile("" ::: "memory");     // one operand kind in flight at a time (register budget)
+            if (p.res_f32 != nullptr) {
+              float4 t4[8];
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp) if (pp < nrows) t4[pp] = *reinterpret_cast<const float4*>(p.res_f32 + off0 + pp * rstep);
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp)
+                if (pp < nrows) { pre[pp].x += t4[pp].x; pre[pp].y += t4[pp].y; pre[pp].z += t4[pp].z; pre[pp].w += t4[pp].w; }
+            }
+            asm volatile("" ::: "memory");
+            if (p.res_planes != nullptr) {
+              uint2 h2[8], l2[8];
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp)
+                if (pp < nrows) {
+                  h2[pp] = *reinterpret_cast<const uint2*>(p.res_planes + off0 + pp * rstep);
+                  l2[pp] = *reinterpret_cast<const uint2*>(p.res_planes + plane + off0 + pp * rstep);
+                }
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp)
+                if (pp < nrows) {
+                  pre[pp].x += p.res_scale * fd_combine((uint16_t)(h2[pp].x & 0xffff), (uint16_t)(l2[pp].x & 0xffff), PREC);
+                  pre[pp].y += p.res_scale * fd_combine((uint16_t)(h2[pp].x >> 16), (uint16_t)(l2[pp].x >> 16), PREC);
+                  pre[pp].z += p.res_scale * fd_combine((uint16_t)(h2[pp].y & 0xffff), (uint16_t)(l2[pp].y & 0xffff), PREC);
+                  pre[pp].w += p.res_scale * fd_combine((uint16_t)(h2[pp].y >> 16), (uint16_t)(l2[pp].y >> 16), PREC);
+                }
+            }
+            asm volatile("" ::: "memory");
+            uint32_t mkbits = 0;
+            if (p.row_mask != nullptr) {
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp)
+                if (pp < nrows && p.row_mask[(size_t)b * p.T + rbase + pp * 4] != 0) mkbits |= 1u << pp;
+            }
+            // the accumulators are fetched only now: keeping them out of the registers while the operand loads are in
+            // flight is what lets 8 rows per lane be outstanding without spilling
+            tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[16]));
+            float4 a[8];
+            warp_transpose_32x32(my_scratch, lane, v, a);
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              a[pp].x = (a[pp].x * p.acc_scale + bias4.x + pre[pp].x) * p.post_scale;
+              a[pp].y = (a[pp].y * p.acc_scale + bias4.y + pre[pp].y) * p.post_scale;
+              a[pp].z = (a[pp].z * p.acc_scale + bias4.z + pre[pp].z) * p.post_scale;
+              a[pp].w = (a[pp].w * p.acc_scale + bias4.w + pre[pp].w) * p.post_scale;
+            }
+            if (p.out_f32 != nullptr && p.out_accum) {       // accumulate launches: one more batch of 8 loads
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp) if (pp < nrows) pre[pp] = *reinterpret_cast<const float4*>(p.out_f32 + off0 + pp * rstep);
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp)
+                if (pp < nrows) { a[pp].x += pre[pp].x; a[pp].y += pre[pp].y; a[pp].z += pre[pp].z; a[pp].w += pre[pp].w; }
+            }
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              if (pp >= nrows) continue;
+              const bool m = (mkbits >> pp) & 1u;
+              const size_t off = off0 + pp * rstep;
+              if (p.out_f32 != nullptr)
+                *reinterpret_cast<float4*>(p.out_f32 + off) = m ? make_float4(0.f, 0.f, 0.f, 0.f) : a[pp];
+              if (p.out_planes != nullptr) {
+                float o4[4] = {a[pp].x, a[pp].y, a[pp].z, a[pp].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float w = o4[i] * p.planes_scale;
+                  if (p.act == FD_ACT_RELU) w = fmaxf(w, 0.f);
+                  else if (p.act == FD_ACT_LRELU) w = w > 0.f ? w : w * p.act_slope;
+                  o4[i] = m ? 0.f : w;
+                }
+                fd_store_planes<4>(p.out_planes, plane, off, o4, PREC);
               }
             }
           } else {
@@ -504,7 +614,7 @@ int launch_inst(const FdTapGemm& p, cudaStream_t stream) {
   const int tiles_t = (p.T + BLOCK_M - 1) / BLOCK_M;
   const int num_tiles = p.B * tiles_t * (p.n_total / BLOCK_N);
   const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tmw, p);
+  kern<<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(tm0, tm1, tmw, p);
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

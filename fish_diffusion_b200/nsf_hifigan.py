@@ -160,6 +160,23 @@ class Generator(nn.Module):
             return N.backend_code(self.backend)
         return N.BACKEND_TC if N.tc_supported_linear(n_total, k_seg, num_seg) else N.BACKEND_SIMT
 
+    @staticmethod
+    def _fold_factor(Ci, Co, K, d):
+        """Time-folding factor of a narrow square conv (1 = keep).  A [T, C] tensor with C = 16 / 32 / 64 is the same
+        memory as [T/F, F*C]; on that view the conv is a block-Toeplitz tap-GEMM with 128 input and output columns and
+        far fewer taps.  Narrow tiles are bound by TMA row rate (32-byte rows) and by the tensor core's poor efficiency
+        at N = 16..64, so trading zero blocks in the weights (tensor pipe is idle there) for 256-byte rows and N = 128
+        wins: always at C = 16, for dilation-1 convs at C = 32, for the 11-tap dilation-1 convs at C = 64."""
+        if Ci != Co:
+            return 1
+        if Ci == 16:
+            return 8
+        if Ci == 32 and d == 1:
+            return 4
+        if Ci == 64 and d == 1 and K >= 11:
+            return 2
+        return 1
+
     def _pack_conv(self, conv, prec, device):
         """Conv1d(Ci->Co, K, dilation d, 'same' padding) -> tap-GEMM weights [Co][K*Ci] + row shifts."""
         w = _effective_weight(conv).detach().to(device=device, dtype=torch.float32)
@@ -167,10 +184,24 @@ class Generator(nn.Module):
         d = conv.dilation[0]
         w2 = w.permute(0, 2, 1).reshape(Co, K * Ci).contiguous()
         s = N.pow2_scale(w2)
-        return dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, Ci=Ci, N=Co,
-                    shifts=[(j - (K - 1) // 2) * d for j in range(K)],
-                    bias=conv.bias.detach().to(device=device, dtype=torch.float32).contiguous(),
-                    backend=self._backend_for(Co, Ci, K))
+        bias = conv.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        offs = [(j - (K - 1) // 2) * d for j in range(K)]
+        pc = dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, Ci=Ci, N=Co, shifts=offs, bias=bias,
+                  backend=self._backend_for(Co, Ci, K))
+        F = self._fold_factor(Ci, Co, K, d)
+        if F > 1 and pc["backend"] == N.BACKEND_TC:
+            # folded row r holds time steps F*r + f: output (fo, n) reads input (s, fi, c) with
+            # F*s + fi = fo + off_j, i.e. s = floor((fo + off_j) / F), fi = (fo + off_j) mod F
+            srows = sorted({(fo + o) // F for fo in range(F) for o in offs})
+            if len(srows) <= 16 and self._backend_for(F * Co, F * Ci, len(srows)) == N.BACKEND_TC:
+                Wf = torch.zeros((F, Co, len(srows), F, Ci), dtype=torch.float32, device=device)
+                for fo in range(F):
+                    for j, o in enumerate(offs):
+                        Wf[fo, :, srows.index((fo + o) // F), (fo + o) % F, :] = w[:, :, j]
+                wf = Wf.reshape(F * Co, len(srows) * F * Ci).contiguous()
+                pc["fold"] = dict(F=F, w=N.pack_weight(wf, prec, s), inv=1.0 / s, Ci=F * Ci, N=F * Co, shifts=srows,
+                                  bias=bias.repeat(F).contiguous(), backend=N.BACKEND_TC)
+        return pc
 
     def _pack_convt(self, conv, prec, device):
         """ConvTranspose1d(Ci->Co, k, stride u, padding p) as a polyphase tap-GEMM: output row q of width u*Co
@@ -223,6 +254,9 @@ class Generator(nn.Module):
 
     # ------------------------------------------------------------------------------------ forward
     def _conv(self, pc, in_planes, B, T, **kw):
+        fold = pc.get("fold")
+        if fold is not None and T % fold["F"] == 0:      # same memory viewed as [T/F, F*C] (see _fold_factor)
+            pc, T = fold, T // fold["F"]
         N.conv_cl(in_planes, pc["w"], B, T, pc["Ci"], pc["N"], pc["shifts"], bias=pc["bias"], w_inv_scale=pc["inv"],
                   prec=self._pack["mma"], backend=pc["backend"], **kw)
 
