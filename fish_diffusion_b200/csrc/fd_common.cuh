@@ -134,6 +134,21 @@ __device__ __forceinline__ float fd_combine(uint16_t hi, uint16_t lo, int prec) 
   return fd_h2f(hi, prec) + fd_h2f(lo, prec);
 }
 
+// two neighbouring channels from their plane words (low half-word -> a, high half-word -> b)
+__device__ __forceinline__ void fd_combine2(uint32_t hi2, uint32_t lo2, int prec, float& a, float& b) {
+  if (prec == FD_F16) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo2));
+    a = h.x + l.x; b = h.y + l.y;
+  } else {
+    a = __uint_as_float(hi2 << 16) + __uint_as_float(lo2 << 16);
+    b = __uint_as_float(hi2 & 0xffff0000u) + __uint_as_float(lo2 & 0xffff0000u);
+  }
+}
+
+// branch-free activation of the linear epilogue: slope = 1 (none), 0 (ReLU) or the LeakyReLU slope
+__device__ __forceinline__ float fd_act(float w, float slope) { return fmaf(slope, fminf(w, 0.f), fmaxf(w, 0.f)); }
+
 // accurate-enough transcendental pieces (relative error ~1e-7; tanh.approx is 1e-3 and is NOT used)
 __device__ __forceinline__ float fd_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fd_tanh(float x) {
@@ -152,26 +167,33 @@ template <int V> struct FdVec16;   // V x uint16
 template <> struct FdVec16<4> { uint2 v; };
 template <> struct FdVec16<8> { uint4 v; };
 
+// two neighbouring channels at once: ONE packed, saturating conversion per plane word (F2FP.SATFINITE.*.PACK_AB)
+// instead of clamp + convert + pack per element.  a -> low half-word, b -> high half-word.  Bit-identical to fd_split
+// for |v| <= 65504 (f16) / all finite v (bf16).
+__device__ __forceinline__ void fd_split2(float a, float b, int prec, uint32_t& hi2, uint32_t& lo2) {
+  if (prec == FD_F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - hf.y), "f"(a - hf.x));
+  } else {
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));
+    const float ha = __uint_as_float(hi2 << 16), hb = __uint_as_float(hi2 & 0xffff0000u);
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - hb), "f"(a - ha));
+  }
+}
+
 template <int V>
 __device__ __forceinline__ void fd_store_planes(uint16_t* planes, size_t plane_elems, size_t off,
                                                 const float (&y)[V], int prec) {
-  uint16_t hi[V], lo[V];
+  uint32_t hi[V / 2], lo[V / 2];
 #pragma unroll
-  for (int i = 0; i < V; ++i) fd_split(y[i], prec, hi[i], lo[i]);
+  for (int i = 0; i < V / 2; ++i) fd_split2(y[2 * i], y[2 * i + 1], prec, hi[i], lo[i]);
   if (V == 4) {
-    uint2 a, b;
-    a.x = hi[0] | ((uint32_t)hi[1] << 16); a.y = hi[2] | ((uint32_t)hi[3] << 16);
-    b.x = lo[0] | ((uint32_t)lo[1] << 16); b.y = lo[2] | ((uint32_t)lo[3] << 16);
-    *reinterpret_cast<uint2*>(planes + off) = a;
-    *reinterpret_cast<uint2*>(planes + plane_elems + off) = b;
+    *reinterpret_cast<uint2*>(planes + off) = make_uint2(hi[0], hi[1]);
+    *reinterpret_cast<uint2*>(planes + plane_elems + off) = make_uint2(lo[0], lo[1]);
   } else {
-    uint4 a, b;
-    a.x = hi[0] | ((uint32_t)hi[1] << 16); a.y = hi[2] | ((uint32_t)hi[3] << 16);
-    a.z = hi[4 % V] | ((uint32_t)hi[5 % V] << 16); a.w = hi[6 % V] | ((uint32_t)hi[7 % V] << 16);
-    b.x = lo[0] | ((uint32_t)lo[1] << 16); b.y = lo[2] | ((uint32_t)lo[3] << 16);
-    b.z = lo[4 % V] | ((uint32_t)lo[5 % V] << 16); b.w = lo[6 % V] | ((uint32_t)lo[7 % V] << 16);
-    *reinterpret_cast<uint4*>(planes + off) = a;
-    *reinterpret_cast<uint4*>(planes + plane_elems + off) = b;
+    *reinterpret_cast<uint4*>(planes + off) = make_uint4(hi[0], hi[1], hi[2 % (V / 2)], hi[3 % (V / 2)]);
+    *reinterpret_cast<uint4*>(planes + plane_elems + off) = make_uint4(lo[0], lo[1], lo[2 % (V / 2)], lo[3 % (V / 2)]);
   }
 }
 

@@ -287,118 +287,136 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
           }
           const float4 bias4 = lds128(bias_addr + 4u * col);
           if (EPI == FD_EPI_RES_SKIP) {
+            // residual columns: x' = (x + y)/sqrt2 on the split planes; skip columns: fp32 accumulation.  32-bit element
+            // offsets (checked on the host), rows past T clamped for the loads and skipped for the stores.
             const bool is_res = n0 < p.C;
+            const uint32_t rowbase = (uint32_t)b * (uint32_t)p.T;
+            const uint32_t cn = (uint32_t)(is_res ? n : n - p.C);
+            const int nrows = rbase < p.T ? min(8, (p.T - rbase + 3) / 4) : 0;
             const size_t plane = (size_t)p.B * p.T * p.C;
-            uint4 op[8];     // residual tile: .xy = hi-plane words, .zw = lo-plane words; skip tile: 4 floats
+            uint32_t eo[8];
 #pragma unroll
-            for (int pp = 0; pp < 8; ++pp) {
-              const int tt = rbase + pp * 4;
-              if (tt < p.T) {
-                const size_t ro = ((size_t)b * p.T + tt) * p.C;
-                if (is_res) {
-                  if (!p.last_layer) {
-                    const uint2 h2 = *reinterpret_cast<const uint2*>(p.x_planes + ro + n);
-                    const uint2 l2 = *reinterpret_cast<const uint2*>(p.x_planes + plane + ro + n);
-                    op[pp] = make_uint4(h2.x, h2.y, l2.x, l2.y);
-                  }
-                } else if (!p.first_layer) {
-                  op[pp] = *reinterpret_cast<const uint4*>(p.skip_f32 + ro + (n - p.C));
+            for (int pp = 0; pp < 8; ++pp)
+              eo[pp] = (rowbase + (uint32_t)min(rbase + pp * 4, p.T - 1)) * (uint32_t)p.C + cn;
+            uint4 op[8];     // residual tile: .xy = hi-plane words, .zw = lo-plane words; skip tile: 4 floats
+            if (is_res) {
+              if (!p.last_layer) {
+                const uint16_t* const xlo = p.x_planes + plane;
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp) {
+                  const uint2 h2 = *reinterpret_cast<const uint2*>(p.x_planes + eo[pp]);
+                  const uint2 l2 = *reinterpret_cast<const uint2*>(xlo + eo[pp]);
+                  op[pp] = make_uint4(h2.x, h2.y, l2.x, l2.y);
                 }
               }
+            } else if (!p.first_layer) {
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp) op[pp] = *reinterpret_cast<const uint4*>(p.skip_f32 + eo[pp]);
             }
             tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
             tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[16]));
             float4 a[8];
             warp_transpose_32x32(my_scratch, lane, v, a);
+            if (is_res) {
+              if (!p.last_layer) {
+                uint16_t* const xo = p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes;
+                uint16_t* const xo_lo = xo + plane;
 #pragma unroll
-            for (int pp = 0; pp < 8; ++pp) {
-              const int tt = rbase + pp * 4;
-              if (tt >= p.T) continue;
-              const size_t ro = ((size_t)b * p.T + tt) * p.C;
-              float y[4] = {a[pp].x * p.acc_scale + bias4.x, a[pp].y * p.acc_scale + bias4.y,
-                            a[pp].z * p.acc_scale + bias4.z, a[pp].w * p.acc_scale + bias4.w};
-              if (is_res) {
-                if (p.last_layer) continue;
-                const uint4 o = op[pp];
-                float x4[4];
-                x4[0] = fd_combine((uint16_t)(o.x & 0xffff), (uint16_t)(o.z & 0xffff), PREC);
-                x4[1] = fd_combine((uint16_t)(o.x >> 16), (uint16_t)(o.z >> 16), PREC);
-                x4[2] = fd_combine((uint16_t)(o.y & 0xffff), (uint16_t)(o.w & 0xffff), PREC);
-                x4[3] = fd_combine((uint16_t)(o.y >> 16), (uint16_t)(o.w >> 16), PREC);
+                for (int pp = 0; pp < 8; ++pp) {
+                  if (pp >= nrows) break;
+                  float x0, x1, x2, x3;
+                  fd_combine2(op[pp].x, op[pp].z, PREC, x0, x1);
+                  fd_combine2(op[pp].y, op[pp].w, PREC, x2, x3);
+                  x0 = (x0 + (a[pp].x * p.acc_scale + bias4.x)) * 0.70710678118654752440f;
+                  x1 = (x1 + (a[pp].y * p.acc_scale + bias4.y)) * 0.70710678118654752440f;
+                  x2 = (x2 + (a[pp].z * p.acc_scale + bias4.z)) * 0.70710678118654752440f;
+                  x3 = (x3 + (a[pp].w * p.acc_scale + bias4.w)) * 0.70710678118654752440f;
+                  uint32_t h0, l0, h1, l1;
+                  fd_split2(x0, x1, PREC, h0, l0);
+                  fd_split2(x2, x3, PREC, h1, l1);
+                  *reinterpret_cast<uint2*>(xo + eo[pp]) = make_uint2(h0, h1);
+                  *reinterpret_cast<uint2*>(xo_lo + eo[pp]) = make_uint2(l0, l1);
+                }
+              }
+            } else {
+              uint16_t* const sk_lo = p.skip_planes + plane;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) x4[i] = (x4[i] + y[i]) * 0.70710678118654752440f;
-                fd_store_planes<4>(p.x_out_planes != nullptr ? p.x_out_planes : p.x_planes, plane, ro + n, x4, PREC);
-              } else {
+              for (int pp = 0; pp < 8; ++pp) {
+                if (pp >= nrows) break;
+                float y0 = a[pp].x * p.acc_scale + bias4.x, y1 = a[pp].y * p.acc_scale + bias4.y;
+                float y2 = a[pp].z * p.acc_scale + bias4.z, y3 = a[pp].w * p.acc_scale + bias4.w;
                 if (!p.first_layer) {
-                  const uint4 o = op[pp];
-                  y[0] += __uint_as_float(o.x); y[1] += __uint_as_float(o.y);
-                  y[2] += __uint_as_float(o.z); y[3] += __uint_as_float(o.w);
+                  y0 += __uint_as_float(op[pp].x); y1 += __uint_as_float(op[pp].y);
+                  y2 += __uint_as_float(op[pp].z); y3 += __uint_as_float(op[pp].w);
                 }
                 if (p.last_layer) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) y[i] *= p.skip_scale;
-                  fd_store_planes<4>(p.skip_planes, plane, ro + (n - p.C), y, PREC);
+                  uint32_t h0, l0, h1, l1;
+                  fd_split2(y0 * p.skip_scale, y1 * p.skip_scale, PREC, h0, l0);
+                  fd_split2(y2 * p.skip_scale, y3 * p.skip_scale, PREC, h1, l1);
+                  *reinterpret_cast<uint2*>(p.skip_planes + eo[pp]) = make_uint2(h0, h1);
+                  *reinterpret_cast<uint2*>(sk_lo + eo[pp]) = make_uint2(l0, l1);
                 } else {
-                  *reinterpret_cast<float4*>(p.skip_f32 + ro + (n - p.C)) = make_float4(y[0], y[1], y[2], y[3]);
+                  *reinterpret_cast<float4*>(p.skip_f32 + eo[pp]) = make_float4(y0, y1, y2, y3);
                 }
               }
             }
           } else if (!C::SPLIT_COLS) {
-            // LINEAR, 64 / 128-column tiles (vocoder convs): this epilogue is bound by the latency of its global
-            // operands, so ALL of a chunk's operand loads (8 rows x 16 bytes per lane and operand kind) are issued up
-            // front -- before the TMEM load and the transposes -- and folded kind by kind into one pre-sum, which keeps
-            // the register cost at one kind in flight regardless of how many kinds a launch uses.
-            const size_t plane = (size_t)p.B * p.T * p.n_total;
-            const size_t off0 = ((size_t)b * p.T + rbase) * p.n_total + n;     // row pp of this lane: + pp * rstep
-            const size_t rstep = (size_t)4 * p.n_total;
+            // LINEAR, 64 / 128-column tiles (vocoder convs).  This epilogue is bound by the latency of its global
+            // operands and by its own instruction count, so: ALL of a chunk's operand loads (8 rows x 16 bytes per lane
+            // and operand kind) are issued up front and folded kind by kind into one pre-sum (register cost = one kind
+            // in flight); the accumulators are fetched from TMEM only afterwards; element offsets are 32-bit (checked on
+            // the host) and rows past T are clamped for the loads / skipped for the stores.
+            const uint32_t rowbase = (uint32_t)b * (uint32_t)p.T;
             const int nrows = rbase < p.T ? min(8, (p.T - rbase + 3) / 4) : 0;  // rows rbase + 4*pp < T
+            uint32_t eo[8];                                                     // element offset of this lane's 4 columns
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp)
+              eo[pp] = (rowbase + (uint32_t)min(rbase + pp * 4, p.T - 1)) * (uint32_t)p.n_total + (uint32_t)n;
             float4 pre[8];
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp) pre[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.addend != nullptr) {
               float4 t4[8];
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp) if (pp < nrows) t4[pp] = *reinterpret_cast<const float4*>(p.addend + off0 + pp * rstep);
+              for (int pp = 0; pp < 8; ++pp) t4[pp] = *reinterpret_cast<const float4*>(p.addend + eo[pp]);
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp)
-                if (pp < nrows) { pre[pp].x += t4[pp].x; pre[pp].y += t4[pp].y; pre[pp].z += t4[pp].z; pre[pp].w += t4[pp].w; }
+              for (int pp = 0; pp < 8; ++pp) { pre[pp].x += t4[pp].x; pre[pp].y += t4[pp].y; pre[pp].z += t4[pp].z; pre[pp].w += t4[pp].w; }
             }
             asm volatile("" ::: "memory");     // one operand kind in flight at a time (register budget)
             if (p.res_f32 != nullptr) {
               float4 t4[8];
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp) if (pp < nrows) t4[pp] = *reinterpret_cast<const float4*>(p.res_f32 + off0 + pp * rstep);
+              for (int pp = 0; pp < 8; ++pp) t4[pp] = *reinterpret_cast<const float4*>(p.res_f32 + eo[pp]);
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp)
-                if (pp < nrows) { pre[pp].x += t4[pp].x; pre[pp].y += t4[pp].y; pre[pp].z += t4[pp].z; pre[pp].w += t4[pp].w; }
+              for (int pp = 0; pp < 8; ++pp) { pre[pp].x += t4[pp].x; pre[pp].y += t4[pp].y; pre[pp].z += t4[pp].z; pre[pp].w += t4[pp].w; }
             }
             asm volatile("" ::: "memory");
             if (p.res_planes != nullptr) {
+              const uint16_t* const lo_base = p.res_planes + (size_t)p.B * p.T * p.n_total;
               uint2 h2[8], l2[8];
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp)
-                if (pp < nrows) {
-                  h2[pp] = *reinterpret_cast<const uint2*>(p.res_planes + off0 + pp * rstep);
-                  l2[pp] = *reinterpret_cast<const uint2*>(p.res_planes + plane + off0 + pp * rstep);
-                }
+              for (int pp = 0; pp < 8; ++pp) {
+                h2[pp] = *reinterpret_cast<const uint2*>(p.res_planes + eo[pp]);
+                l2[pp] = *reinterpret_cast<const uint2*>(lo_base + eo[pp]);
+              }
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp)
-                if (pp < nrows) {
-                  pre[pp].x += p.res_scale * fd_combine((uint16_t)(h2[pp].x & 0xffff), (uint16_t)(l2[pp].x & 0xffff), PREC);
-                  pre[pp].y += p.res_scale * fd_combine((uint16_t)(h2[pp].x >> 16), (uint16_t)(l2[pp].x >> 16), PREC);
-                  pre[pp].z += p.res_scale * fd_combine((uint16_t)(h2[pp].y & 0xffff), (uint16_t)(l2[pp].y & 0xffff), PREC);
-                  pre[pp].w += p.res_scale * fd_combine((uint16_t)(h2[pp].y >> 16), (uint16_t)(l2[pp].y >> 16), PREC);
-                }
+              for (int pp = 0; pp < 8; ++pp) {
+                float r0, r1, r2, r3;
+                fd_combine2(h2[pp].x, l2[pp].x, PREC, r0, r1);
+                fd_combine2(h2[pp].y, l2[pp].y, PREC, r2, r3);
+                pre[pp].x += p.res_scale * r0; pre[pp].y += p.res_scale * r1;
+                pre[pp].z += p.res_scale * r2; pre[pp].w += p.res_scale * r3;
+              }
             }
             asm volatile("" ::: "memory");
             uint32_t mkbits = 0;
             if (p.row_mask != nullptr) {
 #pragma unroll
               for (int pp = 0; pp < 8; ++pp)
-                if (pp < nrows && p.row_mask[(size_t)b * p.T + rbase + pp * 4] != 0) mkbits |= 1u << pp;
+                if (p.row_mask[rowbase + (uint32_t)min(rbase + pp * 4, p.T - 1)] != 0) mkbits |= 1u << pp;
             }
             // the accumulators are fetched only now: keeping them out of the registers while the operand loads are in
-            // flight is what lets 8 rows per lane be outstanding without spilling
+            // flight is what lets 8 rows per lane be outstanding
             tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
             tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
             tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
@@ -414,28 +432,23 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
             }
             if (p.out_f32 != nullptr && p.out_accum) {       // accumulate launches: one more batch of 8 loads
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp) if (pp < nrows) pre[pp] = *reinterpret_cast<const float4*>(p.out_f32 + off0 + pp * rstep);
+              for (int pp = 0; pp < 8; ++pp) pre[pp] = *reinterpret_cast<const float4*>(p.out_f32 + eo[pp]);
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp)
-                if (pp < nrows) { a[pp].x += pre[pp].x; a[pp].y += pre[pp].y; a[pp].z += pre[pp].z; a[pp].w += pre[pp].w; }
+              for (int pp = 0; pp < 8; ++pp) { a[pp].x += pre[pp].x; a[pp].y += pre[pp].y; a[pp].z += pre[pp].z; a[pp].w += pre[pp].w; }
             }
+            const float slope = p.act == FD_ACT_NONE ? 1.f : p.act == FD_ACT_RELU ? 0.f : p.act_slope;
+            uint16_t* const out_lo = p.out_planes + (size_t)p.B * p.T * p.n_total;
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp) {
-              if (pp >= nrows) continue;
-              const bool m = (mkbits >> pp) & 1u;
-              const size_t off = off0 + pp * rstep;
-              if (p.out_f32 != nullptr)
-                *reinterpret_cast<float4*>(p.out_f32 + off) = m ? make_float4(0.f, 0.f, 0.f, 0.f) : a[pp];
+              if (pp >= nrows) break;
+              if ((mkbits >> pp) & 1u) a[pp] = make_float4(0.f, 0.f, 0.f, 0.f);      // masked row: zeros everywhere
+              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + eo[pp]) = a[pp];
               if (p.out_planes != nullptr) {
-                float o4[4] = {a[pp].x, a[pp].y, a[pp].z, a[pp].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float w = o4[i] * p.planes_scale;
-                  if (p.act == FD_ACT_RELU) w = fmaxf(w, 0.f);
-                  else if (p.act == FD_ACT_LRELU) w = w > 0.f ? w : w * p.act_slope;
-                  o4[i] = m ? 0.f : w;
-                }
-                fd_store_planes<4>(p.out_planes, plane, off, o4, PREC);
+                uint32_t h0, l0, h1, l1;
+                fd_split2(fd_act(a[pp].x * p.planes_scale, slope), fd_act(a[pp].y * p.planes_scale, slope), PREC, h0, l0);
+                fd_split2(fd_act(a[pp].z * p.planes_scale, slope), fd_act(a[pp].w * p.planes_scale, slope), PREC, h1, l1);
+                *reinterpret_cast<uint2*>(p.out_planes + eo[pp]) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(out_lo + eo[pp]) = make_uint2(l0, l1);
               }
             }
           } else {
@@ -685,6 +698,9 @@ int fd_tapgemm_tc_supported(const FdTapGemm& p) {
 int fd_tapgemm_tc_launch(const FdTapGemm& p, cudaStream_t stream) {
   int bn, bk;
   pick_cfg(p, &bn, &bk);
+  FD_REQUIRE((long long)p.B * p.T * p.n_total < (1ll << 32),
+             "tapgemm(tc): B*T*n_total = %lld exceeds the 32-bit element offsets of the epilogue",
+             (long long)p.B * p.T * p.n_total);
   FD_REQUIRE(bn != 0 && fd_tapgemm_tc_supported(p),
              "tapgemm(tc): no tensor-core instantiation for n_total=%d k_total=%d epi=%d", p.n_total, p.k_total,
              p.epi);
