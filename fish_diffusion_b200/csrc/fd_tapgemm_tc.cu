@@ -280,7 +280,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
           const int col = half * PER + c + j4;           // first of this lane's 4 columns inside the tile
           const int n = n0 + col;                        // global packed column
           float v[32];
-          constexpr bool LATE_TMEM_LD = EPI == FD_EPI_LINEAR && !C::SPLIT_COLS;   // see the LINEAR branch below
+          constexpr bool LATE_TMEM_LD = EPI == FD_EPI_LINEAR;   // see the LINEAR branch below
           if (!LATE_TMEM_LD) {
             tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
             tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
@@ -360,8 +360,8 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 }
               }
             }
-          } else if (!C::SPLIT_COLS) {
-            // LINEAR, 64 / 128-column tiles (vocoder convs).  This epilogue is bound by the latency of its global
+          } else {
+            // LINEAR (vocoder convs, WaveNet head / tail, data gradients).  This epilogue is bound by the latency of its global
             // operands and by its own instruction count, so: ALL of a chunk's operand loads (8 rows x 16 bytes per lane
             // and operand kind) are issued up front and folded kind by kind into one pre-sum (register cost = one kind
             // in flight); the accumulators are fetched from TMEM only afterwards; element offsets are 32-bit (checked on
@@ -449,71 +449,6 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
                 fd_split2(fd_act(a[pp].z * p.planes_scale, slope), fd_act(a[pp].w * p.planes_scale, slope), PREC, h1, l1);
                 *reinterpret_cast<uint2*>(p.out_planes + eo[pp]) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(out_lo + eo[pp]) = make_uint2(l0, l1);
-              }
-            }
-          } else {
-            // LINEAR
-            const size_t plane = (size_t)p.B * p.T * p.n_total;
-            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
-            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[16]));
-            float4 a[8];
-            warp_transpose_32x32(my_scratch, lane, v, a);
-#pragma unroll
-            for (int hp = 0; hp < 2; ++hp) {          // two groups of 4 passes: bounded register use, 4-deep load batches
-              float4 ad[4], rs[4], pv[4];
-              uint2 rh[4], rl[4];
-              bool mk[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int tt = rbase + (hp * 4 + k) * 4;
-                mk[k] = false;
-                if (tt < p.T) {
-                  const size_t gro = (size_t)b * p.T + tt;
-                  const size_t off = gro * p.n_total + n;
-                  if (p.addend != nullptr) ad[k] = *reinterpret_cast<const float4*>(p.addend + off);
-                  if (p.res_f32 != nullptr) rs[k] = *reinterpret_cast<const float4*>(p.res_f32 + off);
-                  if (p.res_planes != nullptr) {
-                    rh[k] = *reinterpret_cast<const uint2*>(p.res_planes + off);
-                    rl[k] = *reinterpret_cast<const uint2*>(p.res_planes + plane + off);
-                  }
-                  if (p.out_f32 != nullptr && p.out_accum) pv[k] = *reinterpret_cast<const float4*>(p.out_f32 + off);
-                  if (p.row_mask != nullptr) mk[k] = p.row_mask[gro] != 0;
-                }
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int pp = hp * 4 + k;
-                const int tt = rbase + pp * 4;
-                if (tt >= p.T) continue;
-                const size_t off = ((size_t)b * p.T + tt) * p.n_total + n;
-                float y[4] = {a[pp].x * p.acc_scale + bias4.x, a[pp].y * p.acc_scale + bias4.y,
-                              a[pp].z * p.acc_scale + bias4.z, a[pp].w * p.acc_scale + bias4.w};
-                if (p.addend != nullptr) { y[0] += ad[k].x; y[1] += ad[k].y; y[2] += ad[k].z; y[3] += ad[k].w; }
-                if (p.res_f32 != nullptr) { y[0] += rs[k].x; y[1] += rs[k].y; y[2] += rs[k].z; y[3] += rs[k].w; }
-                if (p.res_planes != nullptr) {
-                  y[0] += p.res_scale * fd_combine((uint16_t)(rh[k].x & 0xffff), (uint16_t)(rl[k].x & 0xffff), PREC);
-                  y[1] += p.res_scale * fd_combine((uint16_t)(rh[k].x >> 16), (uint16_t)(rl[k].x >> 16), PREC);
-                  y[2] += p.res_scale * fd_combine((uint16_t)(rh[k].y & 0xffff), (uint16_t)(rl[k].y & 0xffff), PREC);
-                  y[3] += p.res_scale * fd_combine((uint16_t)(rh[k].y >> 16), (uint16_t)(rl[k].y >> 16), PREC);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) y[i] *= p.post_scale;
-                if (p.out_f32 != nullptr) {
-                  if (p.out_accum) { y[0] += pv[k].x; y[1] += pv[k].y; y[2] += pv[k].z; y[3] += pv[k].w; }
-                  if (mk[k]) { y[0] = y[1] = y[2] = y[3] = 0.f; }
-                  *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
-                }
-                if (p.out_planes != nullptr) {
-                  float o4[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    float w = y[i] * p.planes_scale;
-                    if (p.act == FD_ACT_RELU) w = fmaxf(w, 0.f);
-                    else if (p.act == FD_ACT_LRELU) w = w > 0.f ? w : w * p.act_slope;
-                    o4[i] = mk[k] ? 0.f : w;
-                  }
-                  fd_store_planes<4>(p.out_planes, plane, off, o4, PREC);
-                }
               }
             }
           }
