@@ -18,6 +18,7 @@ through the gate-bias tables and its gradient is a column sum of dx.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -109,13 +110,14 @@ class WaveNetTrainFn(torch.autograd.Function):
 
         # Gradient scaling: loss gradients are ~1/numel (1e-6 and below at training shapes), under the fp16 plane
         # range.  The whole backward chain therefore runs on S * gradient with S a power of two that puts
-        # max|d_eps| into [32, 64); every quantity that leaves the chain (weight / bias / conditioner / step-vector
+        # max|d_eps| into [1024, 2048) (32x of head room to the fp16 maximum for the channel sums of the chain, while the lo
+        # planes of gradients 1000x smaller than the maximum stay out of the fp16 subnormals); every quantity that leaves the chain (weight / bias / conditioner / step-vector
         # gradients) is multiplied by 1/S exactly.  `net.grad_scale` (a float) skips the one host sync per backward.
         if getattr(net, "grad_scale", None):
             S = float(net.grad_scale)
         else:
             amax = float(d_eps.detach().abs().max())
-            S = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** math.floor(math.log2(64.0 / amax))
+            S = 1.0 if amax == 0.0 or not math.isfinite(amax) else 2.0 ** math.floor(math.log2(2048.0 / amax))
         inv_S = 1.0 / S
 
         # ---------------------------------------------------------------- helpers
@@ -152,7 +154,8 @@ class WaveNetTrainFn(torch.autograd.Function):
         # Direct weight gradients (fd_wgrad_cl): the tensor core reads both operands MN-major straight from the
         # channels-last planes, so no transposed copies exist on this path; the K-major fold path below it serves the
         # SIMT back end and channel counts that are not multiples of 64.
-        direct = pref == N.BACKEND_TC and C % 64 == 0 and E % 64 == 0 and M % 64 == 0
+        direct = (pref == N.BACKEND_TC and C % 64 == 0 and E % 64 == 0 and M % 64 == 0 and
+                  os.environ.get("FD_WGRAD_DIRECT", "1") != "0")
 
         def wgrad_direct(row_srcs, row_segs, col_srcs, col_segs, out=None):
             return N.wgrad_cl(row_srcs, col_srcs, row_segs, col_segs, B, T, scale=inv_S, prec=mma, out=out)
