@@ -14,7 +14,6 @@
 // fd_tapgemm_tc.cu (TMA producer / MMA issuer / TMEM allocator / 8 epilogue warps, smem ring + 2 TMEM stages).
 #include <cuda.h>
 #include <cstring>
-#include <cstdlib>
 #include "fd_common.cuh"
 #include "fd_host.h"
 #include "fd_tc_ptx.cuh"
@@ -40,7 +39,6 @@ struct FdWgradK {
   int row_C[2], col_C[2];
   float* part;
   float acc_scale;
-  int variant;
 };
 
 // MN-major SW128 operand descriptor (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
@@ -168,10 +166,10 @@ fd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_row0, const __grid_con
     // =========================================================== MMA issuer
     if (lane == 0) {
       const uint32_t fmt = PREC == FD_F16 ? 0u : 1u;
-      const uint32_t majors = (p.variant & 1) ? 0u : ((1u << 15) | (1u << 16));
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | majors |
+      // a_major = b_major = MN (bits 15 / 16): both operands are [time][channel] tiles, channel contiguous
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(WG_BLOCK_M >> 4) << 24);
-      const uint32_t LBO = (p.variant & 2) ? 1024 : NPL * WG_BOX_BYTES, SBO = (p.variant & 2) ? NPL * WG_BOX_BYTES : 1024;
+      constexpr uint32_t LBO = NPL * WG_BOX_BYTES, SBO = 1024;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -357,7 +355,6 @@ extern "C" int fd_wgrad_cl(const fd_wgrad_desc* d, void* stream) {
   p.R = R; p.Cc = Cc;
   p.num_row_seg = d->num_row_seg; p.num_col_seg = d->num_col_seg;
   p.part = d->part; p.acc_scale = d->acc_scale;
-  { const char* v = getenv("FD_WG_VARIANT"); p.variant = v ? atoi(v) : 0; }
   p.m_tiles = (R + WG_BLOCK_M - 1) / WG_BLOCK_M;
   const int bn = Cc % 256 == 0 ? 256 : Cc % 128 == 0 ? 128 : 64;
   p.n_tiles = Cc / bn;

@@ -108,6 +108,23 @@ class SourceModuleHnNSF(nn.Module):
         self.l_tanh = torch.nn.Tanh()
 
 
+def fold_conv_weight(w: torch.Tensor, d: int, F: int):
+    """'same'-padded Conv1d weight w [Co, Ci, K] with dilation d, on the time-folded view [T, C] == [T/F, F*C]:
+    returns (W' [F*Co, S*F*Ci], row shifts [S]) of the equivalent tap-GEMM over folded rows,
+        y'[r, fo*Co + n] = sum_s sum_{fi,c} W'[fo*Co + n, (s, fi, c)] * x'[r + shift_s, fi*Ci + c].
+    Folded row r holds time steps F*r + f, so output sub-step fo reads input time F*r + fo + off_j = F*(r + s) + fi with
+    s = floor((fo + off_j) / F), fi = (fo + off_j) mod F.  Zero padding carries over because item lengths are
+    multiples of F (rows outside [0, T/F) are whole groups of out-of-range steps)."""
+    Co, Ci, K = w.shape
+    offs = [(j - (K - 1) // 2) * d for j in range(K)]
+    srows = sorted({(fo + o) // F for fo in range(F) for o in offs})
+    Wf = torch.zeros((F, Co, len(srows), F, Ci), dtype=w.dtype, device=w.device)
+    for fo in range(F):
+        for j, o in enumerate(offs):
+            Wf[fo, :, srows.index((fo + o) // F), (fo + o) % F, :] = w[:, :, j]
+    return Wf.reshape(F * Co, len(srows) * F * Ci).contiguous(), srows
+
+
 class Generator(nn.Module):
     """NSF-HiFiGAN generator (models.py:353-448) on sm_100a kernels.  `h` is the JSON config (AttrDict)."""
 
@@ -190,15 +207,8 @@ class Generator(nn.Module):
                   backend=self._backend_for(Co, Ci, K))
         F = self._fold_factor(Ci, Co, K, d)
         if F > 1 and pc["backend"] == N.BACKEND_TC:
-            # folded row r holds time steps F*r + f: output (fo, n) reads input (s, fi, c) with
-            # F*s + fi = fo + off_j, i.e. s = floor((fo + off_j) / F), fi = (fo + off_j) mod F
-            srows = sorted({(fo + o) // F for fo in range(F) for o in offs})
+            wf, srows = fold_conv_weight(w, d, F)
             if len(srows) <= 16 and self._backend_for(F * Co, F * Ci, len(srows)) == N.BACKEND_TC:
-                Wf = torch.zeros((F, Co, len(srows), F, Ci), dtype=torch.float32, device=device)
-                for fo in range(F):
-                    for j, o in enumerate(offs):
-                        Wf[fo, :, srows.index((fo + o) // F), (fo + o) % F, :] = w[:, :, j]
-                wf = Wf.reshape(F * Co, len(srows) * F * Ci).contiguous()
                 pc["fold"] = dict(F=F, w=N.pack_weight(wf, prec, s), inv=1.0 / s, Ci=F * Ci, N=F * Co, shifts=srows,
                                   bias=bias.repeat(F).contiguous(), backend=N.BACKEND_TC)
         return pc

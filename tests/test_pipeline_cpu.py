@@ -65,3 +65,32 @@ def test_load_checkpoint_prefix_and_vocoder_keys(tmp_path):
     assert not missing and not unexpected
     for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_time_folded_conv_weight_equals_the_conv():
+    """Host logic of the vocoder's time folding (nsf_hifigan.fold_conv_weight): the block-Toeplitz tap-GEMM on the
+    [T/F, F*C] view reproduces torch's dilated 'same' Conv1d exactly (float64), for every (K, d, F) the packer uses."""
+    import torch
+    from fish_diffusion_b200.nsf_hifigan import Generator, fold_conv_weight
+    g = torch.Generator().manual_seed(0)
+    for C, K, d in [(16, 3, 1), (16, 7, 3), (16, 11, 5), (32, 11, 1), (32, 7, 1), (64, 11, 1), (16, 11, 1)]:
+        F = Generator._fold_factor(C, C, K, d)
+        assert F > 1 and C * F == 128
+        w = torch.randn(C, C, K, generator=g, dtype=torch.float64)
+        x = torch.randn(2, C, 40 * F, generator=g, dtype=torch.float64)          # [B, C, T]
+        ref = torch.nn.functional.conv1d(x, w, padding=(K * d - d) // 2, dilation=d)
+        wf, srows = fold_conv_weight(w, d, F)
+        assert len(srows) <= 16
+        xf = x.transpose(1, 2).reshape(2, 40, F * C)                             # [B, T/F, F*C]: same memory as [B,T,C]
+        yf = torch.zeros(2, 40, F * C, dtype=torch.float64)
+        for si, s in enumerate(srows):
+            seg = torch.zeros_like(xf)
+            lo, hi = max(0, -s), min(40, 40 - s)
+            if hi > lo:
+                seg[:, lo:hi] = xf[:, lo + s:hi + s]
+            yf += seg @ wf[:, si * F * C:(si + 1) * F * C].T
+        got = yf.reshape(2, 40 * F, C).transpose(1, 2)
+        assert torch.allclose(got, ref, atol=1e-12), (C, K, d, float((got - ref).abs().max()))
+    # convs the packer leaves alone
+    assert Generator._fold_factor(128, 128, 11, 1) == 1 and Generator._fold_factor(32, 32, 11, 3) == 1
+    assert Generator._fold_factor(64, 64, 3, 1) == 1 and Generator._fold_factor(16, 32, 3, 1) == 1
