@@ -13,5 +13,6 @@ from .nsf_hifigan import Generator, NsfHifiGAN  # noqa: F401
 from .mel import PitchAdjustableMelSpectrogram, dynamic_range_compression  # noqa: F401
 from .diffsinger import ENCODERS, DiffSinger, NaiveProjectionEncoder, load_checkpoint, pitch_to_scale  # noqa: F401
 from .pipeline import BatchedSynthesizer, plan_batches  # noqa: F401
+from . import formats  # noqa: F401
 
 __version__ = "0.1.0"

@@ -119,15 +119,13 @@ class DiffSinger(nn.Module):
         return out
 
 
-def load_checkpoint(model: nn.Module, checkpoint, device="cuda", strict: bool = False):
+def load_checkpoint(model: nn.Module, checkpoint, device="cuda", strict: bool = False, use_ema: bool = False):
     """Reference ``utils/inference.py:6-32`` semantics: Lightning ``state_dict`` with ``model.`` prefixes, ``vocoder.*``
-    keys dropped, non-strict.  Returns the (missing, unexpected) key lists."""
+    keys dropped, non-strict.  ``use_ema=True`` takes the ``ema_model.*`` copy instead (the weights the reference
+    validates with, diffsinger.py:259-263).  Returns the (missing, unexpected) key lists."""
+    from .formats import lightning_state_dict
     state = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, (str, bytes)) else checkpoint
-    if "state_dict" in state:
-        state = state["state_dict"]
-    state = {k: v for k, v in state.items() if not k.startswith("vocoder.")}
-    if any(k.startswith("model.") for k in state):
-        state = {k[len("model."):]: v for k, v in state.items() if k.startswith("model.")}
+    state = lightning_state_dict(state, "ema_model" if use_ema else "model")
     res = model.load_state_dict(state, strict=strict)
     model.to(device)
     return res.missing_keys, res.unexpected_keys
