@@ -184,7 +184,7 @@ def main():
     g = torch.Generator().manual_seed(1 + rank)
     feats_host = torch.randn(B, T, E, generator=g).pin_memory()
     feats = feats_host.to(dev)
-    torch.manual_seed(2 + rank)
+    torch.manual_seed(2)          # one seed for all ranks: the Philox draws are indexed by the global item (first_item)
 
     def barrier():
         if world > 1:
@@ -192,7 +192,7 @@ def main():
         torch.cuda.synchronize()
 
     def sampler_step():
-        return diff(feats, sampler_interval=interval, noise_predictor="naive")
+        return diff(feats, sampler_interval=interval, noise_predictor="naive", first_item=rank * B)
 
     # ---- device-resident timing
     for _ in range(args.warmup):

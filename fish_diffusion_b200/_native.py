@@ -92,11 +92,12 @@ _SIGS = {
     "fd_wavenet_block_fwd": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 +
                              [c_float, c_float, c_int, c_int, c_int, c_void_p]),
     "fd_conv_cl_fwd": (c_int, [POINTER(ConvDesc), c_void_p]),
-    "fd_ddpm_step": (c_int, [c_void_p] * 5 + [c_longlong] + [c_float] * 7 + [c_ulonglong, c_ulonglong, c_int, c_void_p]),
+    "fd_ddpm_step": (c_int, [c_void_p] * 5 + [c_longlong] + [c_float] * 7 + [c_ulonglong, c_ulonglong, c_ulonglong, c_int,
+                                                                               c_void_p]),
     "fd_lincomb": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p]),
     "fd_affine_cl": (c_int, [c_void_p] * 4 + [c_int, c_longlong, c_int, c_void_p]),
     "fd_q_sample": (c_int, [c_void_p] * 5 + [c_int, c_longlong, c_void_p]),
-    "fd_randn": (c_int, [c_void_p, c_longlong, c_ulonglong, c_ulonglong, c_void_p]),
+    "fd_randn": (c_int, [c_void_p, c_longlong, c_ulonglong, c_ulonglong, c_ulonglong, c_void_p]),
     "fd_sinegen_ws_bytes": (c_size_t, [c_int, c_longlong]),
     "fd_sinegen_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_ulonglong,
                                                 c_void_p]),

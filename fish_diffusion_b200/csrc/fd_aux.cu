@@ -257,7 +257,7 @@ __global__ void k_ddpm_step(const float* __restrict__ x, const float* __restrict
                             const float* __restrict__ noise, float* __restrict__ x_out,
                             uint16_t* __restrict__ x_planes, long long n, float c_recip, float c_recipm1, float c1,
                             float c2, float sigma, float clip_min, float clip_max, unsigned long long seed,
-                            unsigned long long offset, int prec) {
+                            unsigned long long offset, unsigned long long subseq0, int prec) {
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -269,7 +269,7 @@ __global__ void k_ddpm_step(const float* __restrict__ x, const float* __restrict
       fd_load_f32<4>(noise + e, nz);
     } else if (sigma != 0.f) {
       curandStatePhilox4_32_10_t st;
-      curand_init(seed, (unsigned long long)i, offset, &st);
+      curand_init(seed, subseq0 + (unsigned long long)i, offset, &st);
       const float4 g = curand_normal4(&st);
       nz[0] = g.x; nz[1] = g.y; nz[2] = g.z; nz[3] = g.w;
     } else {
@@ -329,12 +329,13 @@ __global__ void k_q_sample(const float* __restrict__ x, const float* __restrict_
   }
 }
 
-__global__ void k_randn(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+__global__ void k_randn(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                        unsigned long long subseq0) {
   const long long n4 = (n + 3) / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     curandStatePhilox4_32_10_t st;
-    curand_init(seed, (unsigned long long)i, offset, &st);
+    curand_init(seed, subseq0 + (unsigned long long)i, offset, &st);
     const float4 g = curand_normal4(&st);
     const float v[4] = {g.x, g.y, g.z, g.w};
     for (int k = 0; k < 4; ++k)
@@ -455,11 +456,12 @@ int fd_wavenet_gate_bias_from_d(const float* d, const float* w1p, const float* b
 
 int fd_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, uint16_t* x_planes,
                  long long n, float c_recip, float c_recipm1, float c1, float c2, float sigma, float clip_min,
-                 float clip_max, unsigned long long seed, unsigned long long offset, int prec, void* stream) {
+                 float clip_max, unsigned long long seed, unsigned long long offset, unsigned long long subseq0,
+                 int prec, void* stream) {
   FD_REQUIRE(n % 4 == 0, "fd_ddpm_step: n=%lld must be a multiple of 4", n);
   k_ddpm_step<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, x_out, x_planes, n, c_recip,
                                                                   c_recipm1, c1, c2, sigma, clip_min, clip_max, seed,
-                                                                  offset, prec);
+                                                                  offset, subseq0, prec);
   FD_LAUNCHED();
   return 0;
 }
@@ -491,8 +493,9 @@ int fd_q_sample(const float* x, const float* noise, const float* a, const float*
   return 0;
 }
 
-int fd_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream) {
-  k_randn<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+int fd_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, unsigned long long subseq0,
+             void* stream) {
+  k_randn<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, subseq0);
   FD_LAUNCHED();
   return 0;
 }

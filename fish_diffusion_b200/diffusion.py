@@ -74,7 +74,7 @@ class NaiveNoisePredictor(nn.Module):
         self._host = None
         return super()._load_from_state_dict(*a, **k)
 
-    def step_cl(self, x, t: int, eps, noise=None, x_planes=None, prec=N.PREC_F16, seed=0, offset=0):
+    def step_cl(self, x, t: int, eps, noise=None, x_planes=None, prec=N.PREC_F16, seed=0, offset=0, subseq0=0):
         """x' = NaiveNoisePredictor.forward(x, t, eps) (noise_predictor.py:73-104) on fp32 tensors of any layout
         (elementwise); in place on x.  `noise` None -> in-kernel Philox."""
         h = self.host_tables()
@@ -83,7 +83,8 @@ class NaiveNoisePredictor(nn.Module):
             N.ptr(x), N.ptr(eps), N.ptr(noise), N.ptr(x), N.ptr(x_planes), x.numel(),
             float(h["sqrt_recip_alphas_cumprod"][t]), float(h["sqrt_recipm1_alphas_cumprod"][t]),
             float(h["posterior_mean_coef1"][t]), float(h["posterior_mean_coef2"][t]), sigma,
-            float(h["clip_min"]), float(h["clip_max"]), seed, offset, prec, N.stream_ptr(x.device)), "fd_ddpm_step")
+            float(h["clip_min"]), float(h["clip_max"]), seed, offset, subseq0, prec, N.stream_ptr(x.device)),
+            "fd_ddpm_step")
         return x
 
 
@@ -210,7 +211,7 @@ class GaussianDiffusion(nn.Module):
         out = torch.empty(shape, dtype=torch.float32, device=device)
         self._philox_calls += 1
         N.check(N.lib().fd_randn(N.ptr(out), out.numel(), self._rng_seed(), self._philox_calls << 20,
-                                 N.stream_ptr(device)), "fd_randn")
+                                 getattr(self, "_subseq0", 0), N.stream_ptr(device)), "fd_randn")
         return out
 
     @staticmethod
@@ -262,6 +263,7 @@ class GaussianDiffusion(nn.Module):
         B, T, E = features.shape
         dev = features.device
         prec = self._prec()
+        self._subseq0 = 0
         if t is None:
             t = torch.randint(0, self.num_timesteps, (B,), device=dev).long()
         with torch.no_grad():
@@ -284,16 +286,20 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def forward(self, features, sampler_interval=None, progress: bool = False, skip_steps: int = 0,
                 original_mel: torch.Tensor = None, noise_predictor: str = None, x_masks: torch.Tensor = None,
-                cond_masks: torch.Tensor = None, x_T: torch.Tensor = None, step_noises=None, seed: int = None):
+                cond_masks: torch.Tensor = None, x_T: torch.Tensor = None, step_noises=None, seed: int = None,
+                first_item: int = 0):
         """Reference contract (diffusion.py:196-313): features [B,T,E] -> mel [B,T,M].
         Extra (parity tests): x_T [B,M,T] replaces the initial randn / the q_sample noise of shallow diffusion,
-        step_noises[i] [B,M,T] replaces the i-th randn_like of the naive predictor."""
+        step_noises[i] [B,M,T] replaces the i-th randn_like of the naive predictor.
+        first_item: index of features[0] inside the global batch.  The in-kernel Philox draws are indexed by the
+        global element, so with the same `seed` a batch sharded over ranks / split into calls of
+        the same T reproduces the unsharded result bit for bit."""
         if seed is not None:
             # reproducible call: Philox streams are (seed, draw index within this call) instead of the running counter
             self._seed_override, self._philox_calls = int(seed), 0
             try:
                 return self.forward(features, sampler_interval, progress, skip_steps, original_mel, noise_predictor,
-                                    x_masks, cond_masks, x_T, step_noises, None)
+                                    x_masks, cond_masks, x_T, step_noises, None, first_item)
             finally:
                 self._seed_override = None
         if sampler_interval is None:
@@ -309,6 +315,7 @@ class GaussianDiffusion(nn.Module):
         prec = self._prec()
         B, T, E = features.shape
         M = self.mel_bins
+        self._subseq0 = int(first_item) * ((T * M + 3) // 4)      # first Philox subsequence (one per 4 elements)
         cmask = None if cond_masks is None else cond_masks.to(torch.uint8).contiguous()
         cond_planes = N.split_nwc(features.to(torch.float32), prec, mask=cmask)       # once per call
         if original_mel is None:
@@ -342,7 +349,7 @@ class GaussianDiffusion(nn.Module):
                 nz = None if step_noises is None else self._to_cl(step_noises[i])
                 self._philox_calls += 1
                 self.naive_noise_predictor.step_cl(x, int(t), eps, noise=nz, x_planes=x_planes, prec=prec, seed=seed,
-                                                   offset=self._philox_calls << 20)
+                                                   offset=self._philox_calls << 20, subseq0=self._subseq0)
             return self.denorm_spec(x)
 
         if noise_predictor == "unipc":

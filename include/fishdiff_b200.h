@@ -129,11 +129,14 @@ int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream);
 /* NaiveNoisePredictor.forward (noise_predictor.py:73-104):
  *   x0 = c_recip*x - c_recipm1*eps ; clamp ; mean = c1*x0 + c2*x ; x' = mean + sigma*noise
  * sigma = [t>0]*exp(0.5*logvar_t) computed by the caller from the bit-exact tables.
- * noise: injected N(0,1) tensor or NULL -> in-kernel Philox4x32-10 (seed, offset).
+ * noise: injected N(0,1) tensor or NULL -> in-kernel Philox4x32-10: elements 4i..4i+3 are the normal4 draw of
+ *   (seed, subsequence subseq0 + i, offset).  subseq0 = index of the first element / 4 inside the GLOBAL batch, so a
+ *   batch sharded over ranks (or split into calls) draws exactly the noise of the unsharded run.
  * writes x_out (fp32, may alias x) and optionally split planes of x' for the next denoiser call. */
 int fd_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out, uint16_t* x_planes,
                  long long n, float c_recip, float c_recipm1, float c1, float c2, float sigma, float clip_min,
-                 float clip_max, unsigned long long seed, unsigned long long offset, int prec, void* stream);
+                 float clip_max, unsigned long long seed, unsigned long long offset, unsigned long long subseq0,
+                 int prec, void* stream);
 /* out = sum_i coef[i] * in[i]  (PLMS noise_predictor.py:118-148, UniPC uni_pc.py:664-680 updates);
  * nterms <= 6; optionally also writes split planes. in[i] may alias out. */
 int fd_lincomb(float* out, uint16_t* out_planes, const float* const* host_in_ptrs, const float* host_coefs,
@@ -145,8 +148,9 @@ int fd_affine_cl(const float* x, float* y, const float* scale, const float* shif
 /* q_sample (diffusion.py:120-127): y = a[b]*x + s[b]*noise, a/s per batch item (device arrays [B]) */
 int fd_q_sample(const float* x, const float* noise, const float* a, const float* s, float* y, int B,
                 long long per_item, void* stream);
-/* fill with N(0,1) from Philox4x32-10 */
-int fd_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, void* stream);
+/* fill with N(0,1) from Philox4x32-10 (same indexing as fd_ddpm_step) */
+int fd_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, unsigned long long subseq0,
+             void* stream);
 
 /* --------------------------------------------------------------- NSF-HiFiGAN source module (a15) */
 /* Generator.forward f0 upsample + SourceModuleHnNSF (models.py:411-415, 201-294, 337-350):

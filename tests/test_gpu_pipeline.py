@@ -41,3 +41,19 @@ def test_batched_synthesizer_matches_direct_padded_batches(golden_cfg):
     mel = diff(feat, x_masks=mask, cond_masks=mask, seed=11)
     assert torch.equal(mel[0, :300], mels[0]) and torch.equal(mel[1, :256], mels[2])
     # (padding frames carry sampler state with eps = 0 there, as in the reference; callers crop by length)
+
+
+def test_sharded_batch_reproduces_unsharded_sampler_bitwise(golden_cfg):
+    """batch sharding has no data-path collective and the Philox draws are indexed by the global element, so
+    items [2,4) sampled alone (first_item=2) equal rows 2..3 of the 4-item run bit for bit (free-running noise)."""
+    wcfg = golden_cfg["WN_TC"]
+    diff = DIFFUSIONS.build(dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **wcfg), mel_channels=64,
+                                 sampler_interval=100, spec_min=[-5.0], spec_max=[0.0], noise_predictor="naive")).to(dev())
+    diff.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic.wavenet_weights(1, **wcfg).items()})
+    g = torch.Generator().manual_seed(9)
+    feats = torch.randn(4, 200, 64, generator=g).to(dev())
+    full = diff(feats, seed=21)
+    lo = diff(feats[:2].contiguous(), seed=21, first_item=0)
+    hi = diff(feats[2:].contiguous(), seed=21, first_item=2)
+    assert torch.equal(full[:2], lo) and torch.equal(full[2:], hi)
+    assert not torch.equal(hi, diff(feats[2:].contiguous(), seed=21))       # without the offset the noise differs

@@ -144,7 +144,7 @@ def test_sampler_free_running_philox_statistics(golden, golden_cfg):
 def test_randn_kernel_moments():
     from fish_diffusion_b200 import _native as N
     out = torch.empty(1 << 22, device=dev())
-    N.check(N.lib().fd_randn(N.ptr(out), out.numel(), 1234, 0, N.stream_ptr(dev())), "randn")
+    N.check(N.lib().fd_randn(N.ptr(out), out.numel(), 1234, 0, 0, N.stream_ptr(dev())), "randn")
     m, s = float(out.mean()), float(out.std())
     k = float(((out - m) ** 4).mean() / s ** 4)
     assert abs(m) < 3e-3 and abs(s - 1) < 3e-3 and abs(k - 3) < 0.05
