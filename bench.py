@@ -307,7 +307,28 @@ def main():
             s_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
             voc["synth_e2e"] = {"B": Bs5, "T": T, "ms": s_ms, "audio_seconds_per_sec": world * Bs5 * audio_s / (s_ms * 1e-3),
                                 "what": "100-eval DDPM sampler + NSF-HiFiGAN (hop 512) per batch, device resident"}
-            del gen, mel
+            del gen
+            # ---- the config the reference's vocoder recipe trains (configs/vocoder_nsf_hifigan.py:31): hop 256
+            try:
+                with open(VOC_CFG_PATH.replace("config_v1.json", "config_v1_256.json")) as f:
+                    h2 = json.load(f)
+                gen2 = Generator(h2, backend=args.backend, precision=args.precision).to(dev)
+                gen2.remove_weight_norm()
+                gen2.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic.generator_weights(4, h2).items()})
+                gen2(mel, f0, seed=1)
+                barrier()
+                ev0.record()
+                gen2(mel, f0, seed=1)
+                ev1.record()
+                barrier()
+                h_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
+                audio2 = T * 256 / 44100.0
+                voc["hop256"] = {"config": "config_v1_256.json (hop 256)", "B": B, "T": T, "ms": h_ms,
+                                 "rtf_agg": world * B * audio2 / (h_ms * 1e-3), "rtf_stream": audio2 / (h_ms * 1e-3)}
+                del gen2
+            except Exception as ex:  # noqa: BLE001
+                voc["hop256"] = {"error": repr(ex)[:300]}
+            del mel
         except Exception as ex:  # noqa: BLE001
             voc = {"error": repr(ex)[:300]}
 
