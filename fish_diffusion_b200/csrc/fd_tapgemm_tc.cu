@@ -4,14 +4,17 @@
 //
 // A (activations) and W (packed weights) are stored as 16-bit split planes (see fd_common.cuh).
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B/64B/32B swizzle, OOB rows zero-filled:
-//                 that is how the conv zero padding and the time shift of each tap are realised)
-//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma kind::f16, 3 products per
-//                 k16 step: hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM)
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B/64B/32B swizzle, OOB rows zero-filled: that is how the
+//                 conv zero padding and the time shift of each tap are realised; the hi and lo planes of an operand
+//                 arrive in one box)
+//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma kind::f16; three products per k16 step
+//                 -- lo*hi + hi*lo + hi*hi -- or one in single-product mode; fp32 accumulation in TMEM)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
-// Pipelines: smem full/empty ring between TMA and MMA; 2 TMEM accumulator stages between MMA and
-// epilogue, so the epilogue of tile i overlaps the mainloop of tile i+1.
+//   warps 4..   : epilogue      (8 warps; 16 for tiles of <= 32 columns): tcgen05.ld 32x32b -> registers -> fused
+//                 epilogue -> global.  256-column tiles: the two warps of a TMEM lane quadrant split the columns;
+//                 narrower tiles: groups of 4 warps take alternate tiles.
+// Pipelines: smem full/empty ring between TMA and MMA; 2 (256 columns) or 4 TMEM accumulator stages between MMA and
+// epilogue, so the epilogue of tile i overlaps the mainloop of the following tiles.
 #include <cuda.h>
 #include "fd_common.cuh"
 #include "fd_tc_ptx.cuh"
