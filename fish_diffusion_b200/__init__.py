@@ -12,6 +12,7 @@ from .diffusion import GaussianDiffusion, NaiveNoisePredictor, PLMSNoisePredicto
 from .nsf_hifigan import Generator, NsfHifiGAN  # noqa: F401
 from .mel import PitchAdjustableMelSpectrogram, dynamic_range_compression  # noqa: F401
 from .diffsinger import ENCODERS, DiffSinger, NaiveProjectionEncoder, load_checkpoint, pitch_to_scale  # noqa: F401
+from .fastspeech import FastSpeech2Encoder  # noqa: F401
 from .pipeline import BatchedSynthesizer, plan_batches  # noqa: F401
 from . import formats  # noqa: F401
 

@@ -328,11 +328,42 @@ def gold_train(ref, out):
             out[f"train_{name}_g_{k}"] = p.grad.numpy()
 
 
+def gold_encoder(ref, out):
+    """FastSpeech2Encoder (modules/encoders/fast_speech.py) with a stub `.builder`: eval-mode outputs for a float-feature
+    and an embedding-input instance, padded batch."""
+    pkg = types.ModuleType("refenc")
+    pkg.__path__ = [f"{REF}/fish_diffusion/modules/encoders"]
+    sys.modules["refenc"] = pkg
+    builder = types.ModuleType("refenc.builder")
+    builder.ENCODERS = _MiniRegistry("encoders")
+    sys.modules["refenc.builder"] = builder
+    fs = _load("refenc.fast_speech", f"{REF}/fish_diffusion/modules/encoders/fast_speech.py", "refenc")
+    res = {}
+    for tag, kw in (("feat", dict(input_size=20)), ("emb", dict(input_size=50, use_embedding_to_input=True))):
+        torch.manual_seed(31)
+        enc = fs.FastSpeech2Encoder(hidden_size=32, num_layers=2, num_heads=2, ffn_kernel_size=9, dropout=0.1, **kw).eval()
+        with torch.no_grad():
+            for prm in enc.parameters():
+                prm.normal_(0, 0.3)
+        g = torch.Generator().manual_seed(32)
+        contents = torch.randn(2, 13, 20, generator=g) if tag == "feat" else torch.randint(0, 50, (2, 13), generator=g)
+        mask = torch.arange(13)[None, :] >= torch.tensor([13, 8])[:, None]
+        with torch.no_grad():
+            y = enc(contents, mask)
+        res[f"enc_{tag}_contents"] = contents.numpy()
+        res[f"enc_{tag}_mask"] = mask.numpy()
+        res[f"enc_{tag}_y"] = y.numpy()
+        for k, v in enc.state_dict().items():
+            res[f"enc_{tag}_sd_{k}"] = v.numpy()
+    out.update(res)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = load_reference()
-    groups = {"schedules": gold_schedules, "wavenet": gold_wavenet, "sampler": gold_sampler, "vocoder": gold_vocoder,
+    groups = {"encoder": gold_encoder,
+              "schedules": gold_schedules, "wavenet": gold_wavenet, "sampler": gold_sampler, "vocoder": gold_vocoder,
               "mel": gold_mel, "train": gold_train}
     only = sys.argv[1:]
     for name, fn in groups.items():

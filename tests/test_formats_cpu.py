@@ -127,3 +127,62 @@ def test_sample_file_collate_and_feature_projection(tmp_path):
     feats = model.forward_features(**{k: v for k, v in kw.items() if k != "mel"})
     assert feats["features"].shape == (3, 50, 32)
     assert feats["x_masks"].shape == (3, 50) and feats["x_masks"][2, 12:].all() and not feats["x_masks"][2, :12].any()
+
+
+@pytest.mark.parametrize("tag,kw", [("feat", dict(input_size=20)), ("emb", dict(input_size=50, use_embedding_to_input=True))])
+def test_fastspeech2_encoder_vs_reference(golden, tag, kw):
+    """ENCODERS['FastSpeech2Encoder'] (config #5's text encoder): same state_dict keys / shapes as the
+    reference module and the same eval-mode output on a padded batch (golden from the unmodified reference)."""
+    import fish_diffusion_b200.fastspeech  # noqa: F401  (registers the encoder)
+    g = golden("encoder")
+    enc = ENCODERS.build(dict(type="FastSpeech2Encoder", hidden_size=32, num_layers=2, num_heads=2, ffn_kernel_size=9,
+                              dropout=0.1, **kw)).eval()
+    ref_sd = {k[len(f"enc_{tag}_sd_"):]: g[k] for k in g if k.startswith(f"enc_{tag}_sd_")}
+    own = enc.state_dict()
+    assert set(own) == set(ref_sd)
+    assert all(tuple(own[k].shape) == ref_sd[k].shape for k in own)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in ref_sd.items()})
+    mask = torch.from_numpy(g[f"enc_{tag}_mask"])
+    with torch.no_grad():
+        y = enc(torch.from_numpy(g[f"enc_{tag}_contents"]), mask).numpy()
+    ref = g[f"enc_{tag}_y"]
+    assert y.shape == ref.shape == (2, 13, 32)
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max(), np.abs(y - ref).max()
+    assert np.all(y[1, 8:] == 0)                                   # padded frames are zeroed
+    # longer than the 5000-position table: the reversed table is rebuilt for the new length
+    enc(torch.zeros(1, 5003, 20) if tag == "feat" else torch.zeros(1, 5003, dtype=torch.long),
+        torch.zeros(1, 5003, dtype=torch.bool))
+    assert enc._pe.shape[1] == 5003
+
+
+def test_svs_assembly_features_cpu():
+    """BASELINE config #5 (svs_baseline.py:18-26): FastSpeech2Encoder over phoneme ids, gathered to mel frames by
+    phones2mel, plus speaker / pitch projections -> features [B, T_mel, 256-like] for the native sampler."""
+    torch.manual_seed(0)
+    model = DiffSinger(dict(
+        text_encoder=dict(type="FastSpeech2Encoder", input_size=40, hidden_size=32, num_layers=2, num_heads=2,
+                          use_embedding_to_input=True),
+        speaker_encoder=dict(type="NaiveProjectionEncoder", input_size=3, output_size=32, use_embedding=True),
+        pitch_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=32),
+        diffusion=dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **WN), mel_channels=16,
+                       sampler_interval=10, spec_min=[-5.0], spec_max=[0.0]))).eval()
+    B, Tph, Tmel = 2, 7, 30
+    contents = torch.randint(1, 40, (B, Tph))
+    contents_lens = torch.tensor([7, 5])
+    mel_lens = torch.tensor([30, 22])
+    phones2mel = torch.sort(torch.randint(0, 5, (B, Tmel)), dim=1).values
+    pitches = 100 + 50 * torch.rand(B, Tmel, 1)
+    with torch.no_grad():
+        out = model.forward_features(speakers=torch.tensor([0, 2]), contents=contents, contents_lens=contents_lens,
+                                     contents_max_len=Tph, mel_lens=mel_lens, mel_max_len=Tmel, pitches=pitches,
+                                     phones2mel=phones2mel)
+        enc = model.text_encoder(contents, DiffSinger.get_mask_from_lengths(contents_lens, Tph))
+    f = out["features"]
+    assert f.shape == (B, Tmel, 32) and out["x_masks"].shape == (B, Tmel)
+    # frame t of item b carries phoneme phones2mel[b,t]'s encoding (+ speaker + pitch), padded frames only the additions
+    spk = model.speaker_encoder(torch.tensor([0, 2]))[:, None, :]
+    pit = model.pitch_encoder(pitches)
+    b, t = 1, 10
+    want = enc[b, phones2mel[b, t]] + spk[b, 0] + pit[b, t]
+    assert torch.allclose(f[b, t], want, atol=1e-5)
+    assert torch.allclose(f[1, 25], spk[1, 0] + pit[1, 25], atol=1e-5)
