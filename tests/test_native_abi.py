@@ -73,3 +73,20 @@ def test_product_does_not_import_oracle():
             if fn.endswith(".py"):
                 with open(os.path.join(dirpath, fn)) as f:
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read(), flags=re.M), fn
+
+
+def test_precision_codes_and_wgrad_shape_rule():
+    """Host-side parsing of the precision strings (storage precision vs. GEMM arithmetic flag) and the shape rule of the
+    direct weight-gradient kernel -- no device calls."""
+    from fish_diffusion_b200 import _native as N
+    assert N.prec_code("f16") == N.prec_code("f16x1") == N.prec_code("half") == N.PREC_F16
+    assert N.prec_code("bf16") == N.prec_code("bf16x1") == N.PREC_BF16
+    assert N.mma_code("f16") == N.PREC_F16 and N.mma_code("bf16") == N.PREC_BF16
+    assert N.mma_code("f16x1") == (N.PREC_F16 | N.PREC_SINGLE) and N.mma_code("BF16x1") == (N.PREC_BF16 | N.PREC_SINGLE)
+    with pytest.raises(ValueError):
+        N.prec_code("fp8")
+    assert N.wgrad_supported([(0, 0, 1024)], [(0, -4, 0, 512), (0, 0, 0, 512), (0, 4, 0, 512), (1, 0, 0, 256)])
+    assert N.wgrad_supported([(0, 0, 512), (1, 0, 512)], [(0, 0, 0, 512)])
+    assert not N.wgrad_supported([(0, 0, 96)], [(0, 0, 0, 64)])                    # 96 is not a multiple of 64
+    assert not N.wgrad_supported([(0, 0, 64)] * 3, [(0, 0, 0, 64)])                # at most two row segments
+    assert not N.wgrad_supported([(0, 0, 64)], [(0, 0, 0, 64)] * 9)                # at most eight column segments
