@@ -244,7 +244,9 @@ int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_pla
 int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T, int N, float scale, int prec,
               void* stream);
 /* out[edge][b][n] += scale * sum_t planes[b,t,n] over t in [0,e) (edge 0) and [T-e,T) (edge 1); out zero-initialised
- * by the caller (edge terms of the step-vector contribution to the dilated-conv weight gradient) */
+ * by the caller.  Autograd of `conv_layer(x + diffusion_step)` (modules/wavenet.py:107-111): the step vector d is added
+ * before the zero-padded conv, so d(W_tap)/ += (sum over the steps where that tap reads inside [0,T) of dy) (x) d; the
+ * sums are the full column sums minus these edge sums. */
 int fd_colsum_edges(const uint16_t* planes, float* out, int B, int T, int N, int e, float scale, int prec,
                     void* stream);
 
