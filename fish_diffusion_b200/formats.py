@@ -34,6 +34,35 @@ def lightning_state_dict(ckpt: Mapping, part: str = "model") -> Dict[str, torch.
     return out
 
 
+def load_pretrained(model: torch.nn.Module, ckpt: Mapping, has_ema: bool = False) -> Dict[str, List[str]]:
+    """Warm start from a Lightning checkpoint with the rules of `tools/diffusion/train.py:47-95` (`--pretrained`),
+    for `model` = the `DiffSinger` module (Lightning's `.model`):
+      * `vocoder.*` keys are dropped;
+      * a checkpoint that carries `ema_model.*` while the run keeps no EMA (`has_ema=False`) contributes its EMA weights
+        as the model weights;
+      * a speaker-embedding table of another size is dropped (rebuilt from scratch), not an error;
+      * loading is non-strict, but every unexpected key must be explained by the predictor-buffer drift of old
+        checkpoints (buffers stored as `diffusion.<name>` instead of `diffusion.naive_noise_predictor.<name>`).
+    Returns {"missing": [...], "unexpected": [...], "dropped": [...]}."""
+    sd = dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
+    sd = {k: v for k, v in sd.items() if not k.startswith("vocoder.")}
+    if not has_ema and any(k.startswith("ema_model.") for k in sd):
+        sd = {"model." + k[len("ema_model."):]: v for k, v in sd.items() if k.startswith("ema_model.")}
+    sd = lightning_state_dict(sd, "model")
+    dropped = []
+    spk = "speaker_encoder.embedding.weight"
+    own = model.state_dict()
+    if spk in sd and spk in own and sd[spk].shape != own[spk].shape:
+        del sd[spk]
+        dropped.append(spk)
+    res = model.load_state_dict(sd, strict=False)
+    explained = {k.replace(".naive_noise_predictor.", ".") for k in res.missing_keys}
+    stray = sorted(set(res.unexpected_keys) - explained)
+    if stray:
+        raise KeyError(f"unexpected keys in the checkpoint: {stray[:8]}{' ...' if len(stray) > 8 else ''}")
+    return {"missing": list(res.missing_keys), "unexpected": list(res.unexpected_keys), "dropped": dropped}
+
+
 def diff_svc_key(fish_key: str) -> str:
     """Diff-SVC name of a `GaussianDiffusion.state_dict()` key (diff_svc_converter.py:49-56): the ConvNorm / LinearNorm
     wrappers did not exist there and the dilated conv was called `dilated_conv`."""

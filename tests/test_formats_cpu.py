@@ -186,3 +186,38 @@ def test_svs_assembly_features_cpu():
     want = enc[b, phones2mel[b, t]] + spk[b, 0] + pit[b, t]
     assert torch.allclose(f[b, t], want, atol=1e-5)
     assert torch.allclose(f[1, 25], spk[1, 0] + pit[1, 25], atol=1e-5)
+
+
+def test_load_pretrained_rules():
+    """tools/diffusion/train.py:47-95: EMA weights stand in when the run has no EMA, a speaker table of another size is
+    dropped, old predictor-buffer names are tolerated, anything else unexpected is an error."""
+    mk = lambda spk: DiffSinger(dict(
+        text_encoder=dict(type="NaiveProjectionEncoder", input_size=32, output_size=32),
+        speaker_encoder=dict(type="NaiveProjectionEncoder", input_size=spk, output_size=32, use_embedding=True),
+        diffusion=dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **WN), mel_channels=16,
+                       sampler_interval=10, spec_min=[-5.0], spec_max=[0.0])))
+    torch.manual_seed(7)
+    src, dst = mk(4), mk(6)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.normal_()
+    sd = src.state_dict()
+    ck = {"state_dict": {**{"model." + k: torch.zeros_like(v) for k, v in sd.items()},
+                         **{"ema_model." + k: v for k, v in sd.items()}, "vocoder.x": torch.zeros(1)}}
+    # an old checkpoint: predictor buffers directly under `diffusion.`
+    old = {}
+    for k, v in ck["state_dict"].items():
+        old[k.replace(".naive_noise_predictor.", ".")] = v
+    rep = formats.load_pretrained(dst, {"state_dict": old})
+    assert rep["dropped"] == ["speaker_encoder.embedding.weight"]
+    assert all(".naive_noise_predictor." in k or k == "speaker_encoder.embedding.weight" for k in rep["missing"])
+    w = "diffusion.denoise_fn.residual_layers.0.conv_layer.conv.weight"
+    assert torch.equal(dst.state_dict()[w], sd[w])                 # the EMA copy, not the zeroed `model.` copy
+    assert dst.speaker_encoder.embedding.weight.shape[0] == 6      # own table kept
+    # with an EMA in the run the `model.` weights are taken
+    formats.load_pretrained(dst, ck, has_ema=True)
+    assert float(dst.state_dict()[w].abs().sum()) == 0.0
+    bad = dict(ck["state_dict"])
+    bad["ema_model.diffusion.denoise_fn.bogus"] = torch.zeros(1)
+    with pytest.raises(KeyError, match="unexpected"):
+        formats.load_pretrained(dst, {"state_dict": bad})
