@@ -253,7 +253,12 @@ def main():
         roof = {"bound": "tensor", "kernel": f"fd_tapgemm_{backend_name}<gate> (WaveNet GEMM1)", "achieved": ach,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
-                "traffic": None, "algorithmic_flops_per_launch": g1_flops, "avg_launch_ms": t1 * 1e3,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+                # (profiles/r01b_ncu_full_summary.json: 402.2 + 228.6 MB); only valid for the shape it was taken on
+                "traffic": 630806528 if (B, T, args.precision, backend_name) == (32, 4000, "f16", "tc") else None,
+                "traffic_unit": "bytes per launch (ncu, profiles/r01b_ncu_full_summary.json)",
+                "algorithmic_bytes_per_launch": 4 * B * T * (512 + 256 + 512),
+                "algorithmic_flops_per_launch": g1_flops, "avg_launch_ms": t1 * 1e3,
                 "mma_flops_per_launch": (1 if args.precision.lower().endswith("x1") else 3) * g1_flops if backend_name == "tc" else None,
                 "note": "fp32 parity is emulated with 3 fp16 tensor-core products per algorithmic product; "
                         "tensor-pipe utilisation is ~3x frac",
