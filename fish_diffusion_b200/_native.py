@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ubyte, c_ulonglong, c_void_p
 
 import torch
@@ -78,6 +79,7 @@ _SIGS = {
     "fd_reduce_batch": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_float, c_void_p]),
     "fd_abi_version": (c_int, []),
     "fd_last_error": (c_char_p, []),
+    "fd_set_device": (None, [c_int]),
     "fd_launch_count": (c_longlong, []),
     "fd_tc_supported_linear": (c_int, [c_int, c_int, c_int]),
     "fd_prof_enable": (None, [c_int]),
@@ -149,8 +151,20 @@ def ptr(t):
     return t.data_ptr()
 
 
+_tls = threading.local()
+
+
 def stream_ptr(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Current torch stream of `device` as a raw cudaStream_t.  Also tells the library which device the following
+    call targets (fd_set_device, thread-local on both sides), so tensors on a non-current device work."""
+    if device is None or getattr(device, "index", None) is None:
+        idx = torch.cuda.current_device()
+    else:
+        idx = device.index
+    if getattr(_tls, "dev", None) != idx:
+        lib().fd_set_device(idx)
+        _tls.dev = idx
+    return torch.cuda.current_stream(idx).cuda_stream
 
 
 def require_cuda(t, name="tensor"):

@@ -66,6 +66,30 @@ int run(const FdTapGemm& p, int backend, cudaStream_t st) {
 
 void fd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+namespace { thread_local int g_target_dev = -1; int g_sms[FD_MAX_DEVICES] = {0}; }
+
+FdDeviceGuard::FdDeviceGuard() {
+  if (g_target_dev < 0) return;
+  if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+  if (prev != g_target_dev && cudaSetDevice(g_target_dev) == cudaSuccess) switched = true;
+}
+FdDeviceGuard::~FdDeviceGuard() {
+  if (switched) cudaSetDevice(prev);
+}
+int fd_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FD_MAX_DEVICES) dev = 0;
+  return dev;
+}
+int fd_device_sms(int dev) {
+  if (g_sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sms[dev] = n;
+  }
+  return g_sms[dev];
+}
+
 extern "C" {
 
 void fd_set_error(const char* fmt, ...) {
@@ -76,6 +100,7 @@ void fd_set_error(const char* fmt, ...) {
 }
 
 const char* fd_last_error(void) { return g_err; }
+void fd_set_device(int device) { g_target_dev = (device >= 0 && device < FD_MAX_DEVICES) ? device : -1; }
 int fd_abi_version(void) { return FD_ABI_VERSION; }
 long long fd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -121,6 +146,7 @@ int fd_wavenet_block_fwd(uint16_t* x_planes, const uint16_t* cond_planes, uint16
                          int gb_bstride, const float* b2, float* skip_f32, uint16_t* skip_planes, float skip_scale,
                          int B, int T, int C, int E, int dilation, int gate_tile, float w1_inv_scale,
                          float w2_inv_scale, int flags, int prec, int backend, void* stream) {
+  FD_DEVICE_GUARD();
   return wavenet_block(x_planes, nullptr, cond_planes, z_planes, nullptr, w1, w2, gb_full, gb_lo, gb_hi, gb_bstride, b2,
                        skip_f32, skip_planes, skip_scale, B, T, C, E, dilation, gate_tile, w1_inv_scale, w2_inv_scale,
                        flags, prec, backend, stream);
@@ -132,6 +158,7 @@ int fd_wavenet_block_fwd_train(const uint16_t* x_planes, uint16_t* x_out_planes,
                                const float* b2, float* skip_f32, uint16_t* skip_planes, float skip_scale, int B, int T,
                                int C, int E, int dilation, int gate_tile, float w1_inv_scale, float w2_inv_scale,
                                int flags, int prec, int backend, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(x_out_planes != nullptr && y_planes != nullptr, "fd_wavenet_block_fwd_train: x_out / y planes required");
   return wavenet_block(x_planes, x_out_planes, cond_planes, z_planes, y_planes, w1, w2, gb_full, gb_lo, gb_hi,
                        gb_bstride, b2, skip_f32, skip_planes, skip_scale, B, T, C, E, dilation, gate_tile, w1_inv_scale,
@@ -182,6 +209,7 @@ static int wavenet_block(const uint16_t* x_planes, uint16_t* x_out_planes, const
 }
 
 int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(d != nullptr, "fd_conv_cl_fwd: null descriptor");
   FD_REQUIRE(d->ntaps >= 1 && d->ntaps <= FD_MAX_SEG, "fd_conv_cl_fwd: ntaps=%d out of range", d->ntaps);
   FD_REQUIRE(d->B > 0 && d->T > 0 && d->Cin > 0 && d->N > 0, "fd_conv_cl_fwd: bad shape");
@@ -204,6 +232,7 @@ int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream) {
 int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
                     int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, int prec,
                     int backend, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(n_fft % 64 == 0 && hop % 8 == 0 && NB % 128 == 0, "fd_stft_mag_fwd: n_fft=%d hop=%d NB=%d unsupported",
              n_fft, hop, NB);
   const long long pitch = (Np + 7) / 8 * 8;
@@ -222,6 +251,7 @@ int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag
 }
 
 int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(d != nullptr, "fd_gemm_cl_fwd: null descriptor");
   FD_REQUIRE(d->num_seg >= 1 && d->num_seg <= FD_MAX_SEG, "fd_gemm_cl_fwd: num_seg=%d out of range", d->num_seg);
   FD_REQUIRE(d->B > 0 && d->T > 0 && d->n_total > 0 && d->k_total > 0, "fd_gemm_cl_fwd: bad shape");

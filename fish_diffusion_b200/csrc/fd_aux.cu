@@ -363,6 +363,7 @@ extern "C" {
 
 int fd_split_ncw(const float* src, const uint8_t* mask, uint16_t* planes, int B, int C, int T, int prec,
                  void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(B > 0 && C > 0 && T > 0, "fd_split_ncw: bad shape B=%d C=%d T=%d", B, C, T);
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   k_split_ncw<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, planes, B, C, T, prec);
@@ -372,6 +373,7 @@ int fd_split_ncw(const float* src, const uint8_t* mask, uint16_t* planes, int B,
 
 int fd_split_nwc(const float* src, const uint8_t* mask, uint16_t* planes, int B, int T, int C, float scale,
                  int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(C % 4 == 0, "fd_split_nwc: C=%d must be a multiple of 4", C);
   const long long rows = (long long)B * T;
   k_split_nwc<<<grid_for(rows * C / 4), 256, 0, (cudaStream_t)stream>>>(src, mask, planes, rows, C, scale, prec);
@@ -380,6 +382,7 @@ int fd_split_nwc(const float* src, const uint8_t* mask, uint16_t* planes, int B,
 }
 
 int fd_transpose_nwc_to_ncw(const float* src, float* dst, int B, int T, int C, void* stream) {
+  FD_DEVICE_GUARD();
   dim3 grid((C + 31) / 32, (T + 31) / 32, B), block(32, 8);
   k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, T, C);
   FD_LAUNCHED();
@@ -387,6 +390,7 @@ int fd_transpose_nwc_to_ncw(const float* src, float* dst, int B, int T, int C, v
 }
 
 int fd_transpose_ncw_to_nwc(const float* src, float* dst, int B, int C, int T, void* stream) {
+  FD_DEVICE_GUARD();
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, T);
   FD_LAUNCHED();
@@ -394,6 +398,7 @@ int fd_transpose_ncw_to_nwc(const float* src, float* dst, int B, int C, int T, v
 }
 
 int fd_pack_weight(const float* w, uint16_t* planes, long long n_elems, float scale, int prec, void* stream) {
+  FD_DEVICE_GUARD();
   k_pack_weight<<<grid_for(n_elems), 256, 0, (cudaStream_t)stream>>>(w, planes, n_elems, scale, prec);
   FD_LAUNCHED();
   return 0;
@@ -402,6 +407,7 @@ int fd_pack_weight(const float* w, uint16_t* planes, long long n_elems, float sc
 int fd_wavenet_pack_layers(const float* const* conv_w, const float* const* cond_w, const float* const* out_w,
                            const float* scales, float* w1p_f32, uint16_t* w1, uint16_t* w2, uint16_t* w1t, uint16_t* wct,
                            uint16_t* w2t, int L, int C, int E, int gate_half, int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(L > 0 && C > 0 && E > 0 && gate_half > 0 && C % gate_half == 0, "fd_wavenet_pack_layers: bad shape");
   FD_REQUIRE(conv_w && cond_w && out_w && scales && w1p_f32 && w1 && w2, "fd_wavenet_pack_layers: null pointer");
   FD_REQUIRE((w1t == nullptr) == (wct == nullptr) && (w1t == nullptr) == (w2t == nullptr),
@@ -418,6 +424,7 @@ int fd_wavenet_pack_layers(const float* const* conv_w, const float* const* cond_
 
 int fd_wavenet_step_mlp(const float* steps, const float* w0, const float* b0, const float* w1, const float* b1,
                         float* s_out, float* ws, int Bs, int C, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(C % 2 == 0 && C >= 4, "fd_wavenet_step_mlp: bad C=%d", C);
   cudaStream_t st = (cudaStream_t)stream;
   float* emb = ws;                 // [Bs][C]
@@ -434,6 +441,7 @@ int fd_wavenet_step_mlp(const float* steps, const float* w0, const float* b0, co
 int fd_wavenet_gate_bias(const float* s, const float* wd, const float* bd, const float* w1p, const float* bias_sum,
                          float* gb_full, float* gb_lo, float* gb_hi, float* ws, int L, int Bs, int C, int KT,
                          void* stream) {
+  FD_DEVICE_GUARD();
   cudaStream_t st = (cudaStream_t)stream;
   // d[bs][l][c] = Wd[l][c][:] . s[bs] + bd[l][c]
   k_small_linear<<<(L * C * 32 + 255) / 256, 256, 0, st>>>(s, wd, bd, ws, Bs, C, L * C, C, 0);
@@ -447,6 +455,7 @@ int fd_wavenet_gate_bias(const float* s, const float* wd, const float* bd, const
 
 int fd_wavenet_gate_bias_from_d(const float* d, const float* w1p, const float* bias_sum, float* gb_full, float* gb_lo,
                                 float* gb_hi, int L, int Bs, int C, int KT, void* stream) {
+  FD_DEVICE_GUARD();
   const long long warps = (long long)L * Bs * 2 * C;
   k_gate_bias<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, w1p, bias_sum, gb_full, gb_lo,
                                                                                        gb_hi, L, Bs, C, KT);
@@ -458,6 +467,7 @@ int fd_ddpm_step(const float* x, const float* eps, const float* noise, float* x_
                  long long n, float c_recip, float c_recipm1, float c1, float c2, float sigma, float clip_min,
                  float clip_max, unsigned long long seed, unsigned long long offset, unsigned long long subseq0,
                  int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(n % 4 == 0, "fd_ddpm_step: n=%lld must be a multiple of 4", n);
   k_ddpm_step<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, x_out, x_planes, n, c_recip,
                                                                   c_recipm1, c1, c2, sigma, clip_min, clip_max, seed,
@@ -468,6 +478,7 @@ int fd_ddpm_step(const float* x, const float* eps, const float* noise, float* x_
 
 int fd_lincomb(float* out, uint16_t* out_planes, const float* const* host_in_ptrs, const float* host_coefs,
                int nterms, long long n, int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(nterms >= 1 && nterms <= 6, "fd_lincomb: nterms=%d out of range", nterms);
   FD_REQUIRE(n % 4 == 0, "fd_lincomb: n=%lld must be a multiple of 4", n);
   LincombArgs a;
@@ -480,6 +491,7 @@ int fd_lincomb(float* out, uint16_t* out_planes, const float* const* host_in_ptr
 
 int fd_affine_cl(const float* x, float* y, const float* scale, const float* shift, int nparam, long long rows,
                  int C, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(nparam == 1 || nparam == C, "fd_affine_cl: nparam=%d must be 1 or C=%d", nparam, C);
   k_affine_cl<<<grid_for(rows * C), 256, 0, (cudaStream_t)stream>>>(x, y, scale, shift, nparam, rows * C, C);
   FD_LAUNCHED();
@@ -488,6 +500,7 @@ int fd_affine_cl(const float* x, float* y, const float* scale, const float* shif
 
 int fd_q_sample(const float* x, const float* noise, const float* a, const float* s, float* y, int B,
                 long long per_item, void* stream) {
+  FD_DEVICE_GUARD();
   k_q_sample<<<grid_for(B * per_item), 256, 0, (cudaStream_t)stream>>>(x, noise, a, s, y, B * per_item, per_item);
   FD_LAUNCHED();
   return 0;
@@ -495,12 +508,14 @@ int fd_q_sample(const float* x, const float* noise, const float* a, const float*
 
 int fd_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, unsigned long long subseq0,
              void* stream) {
+  FD_DEVICE_GUARD();
   k_randn<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, subseq0);
   FD_LAUNCHED();
   return 0;
 }
 
 int fd_log_clamp(const float* x, float* y, long long n, float clip, float out_scale, void* stream) {
+  FD_DEVICE_GUARD();
   k_log_clamp<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, clip, out_scale);
   FD_LAUNCHED();
   return 0;

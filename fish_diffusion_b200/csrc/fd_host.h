@@ -16,3 +16,17 @@ void fd_count_launch(int n);
       return -1;                                                                               \
     }                                                                                          \
   } while (0)
+
+// ---- device handling.  The binding names the device its tensors live on (fd_set_device, thread-local); every entry
+// point opens with FD_DEVICE_GUARD(), which makes that device current for the duration of the call and restores the
+// caller's afterwards.  Per-device facts (SM count, max-dynamic-smem attribute of a kernel) are cached per device.
+struct FdDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  FdDeviceGuard();
+  ~FdDeviceGuard();
+};
+#define FD_DEVICE_GUARD() FdDeviceGuard _fd_device_guard
+constexpr int FD_MAX_DEVICES = 64;
+int fd_current_device();          // cudaGetDevice (clamped to [0, FD_MAX_DEVICES))
+int fd_device_sms(int dev);       // multiprocessor count, cached

@@ -17,6 +17,7 @@
 // epilogue, so the epilogue of tile i overlaps the mainloop of the following tiles.
 #include <cuda.h>
 #include "fd_common.cuh"
+#include "fd_host.h"
 #include "fd_tc_ptx.cuh"
 
 namespace {
@@ -534,7 +535,6 @@ int make_w_map(CUtensorMap* m, const uint16_t* ptr, int N, int K, int block_n, i
   return 0;
 }
 
-int g_num_sms = 0;
 
 template <int BLOCK_N, int BLOCK_K, int EPI, int PREC, int NPL>
 int launch_inst(const FdTapGemm& p, cudaStream_t stream) {
@@ -552,16 +552,13 @@ int launch_inst(const FdTapGemm& p, cudaStream_t stream) {
   if (rc) return rc;
 
   auto kern = fd_tapgemm_tc_kernel<BLOCK_N, BLOCK_K, EPI, PREC, NPL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[FD_MAX_DEVICES] = {false};   // the max-dynamic-smem attribute is per device
+  const int dev = fd_current_device();
+  if (!attr_set[dev]) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    FD_CHECK_CUDA(cudaGetDevice(&dev));
-    FD_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = fd_device_sms(dev);
   const int tiles_t = (p.T + BLOCK_M - 1) / BLOCK_M;
   const int num_tiles = p.B * tiles_t * (p.n_total / BLOCK_N);
   const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;

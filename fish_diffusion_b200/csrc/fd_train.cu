@@ -162,6 +162,7 @@ extern "C" {
 int fd_fold_transpose(const uint16_t* src_planes, const float* src_f32, const uint16_t* aux_planes, const float* addvec,
                       int add_bstride, uint16_t* dst, int B, int T, int C, int Tp, int pad, float scale, int mode,
                       int gate_tile, int prec, int dst_rows, int dst_row0, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(Tp >= T + pad && pad >= 0, "fd_fold_transpose: Tp=%d too small for T=%d pad=%d", Tp, T, pad);
   if (dst_rows <= 0) { dst_rows = C; dst_row0 = 0; }
   FD_REQUIRE(dst_row0 >= 0 && dst_row0 + C <= dst_rows, "fd_fold_transpose: rows [%d,%d) outside the %d-row destination",
@@ -184,6 +185,7 @@ int fd_fold_transpose(const uint16_t* src_planes, const float* src_f32, const ui
 
 int fd_gate_bwd(const float* dz, const uint16_t* y_planes, uint16_t* dy_planes, long long rows, int C, int gate_tile,
                 int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(C % 4 == 0 && gate_tile % 8 == 0, "fd_gate_bwd: C=%d gate_tile=%d unsupported", C, gate_tile);
   k_gate_bwd<<<grid1d(rows * C / 4), 256, 0, (cudaStream_t)stream>>>(dz, y_planes, dy_planes, rows, C, gate_tile, prec);
   FD_LAUNCHED();
@@ -192,6 +194,7 @@ int fd_gate_bwd(const float* dz, const uint16_t* y_planes, uint16_t* dy_planes, 
 
 int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_planes, long long n, float scale, int prec,
                 void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(n % 4 == 0, "fd_relu_bwd: n=%lld must be a multiple of 4", n);
   k_relu_bwd<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>(grad, act_planes, out_planes, n, scale, prec);
   FD_LAUNCHED();
@@ -200,6 +203,7 @@ int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_pla
 
 int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T, int N, float scale, int prec,
               void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE((planes != nullptr) != (f32 != nullptr), "fd_colsum: exactly one of planes / f32 must be given");
   const int rows_per_block = 128;
   dim3 grid((N + 127) / 128, (T + rows_per_block - 1) / rows_per_block, B);
@@ -210,6 +214,7 @@ int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T
 
 int fd_colsum_edges(const uint16_t* planes, float* out, int B, int T, int N, int e, float scale, int prec,
                     void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(planes != nullptr && out != nullptr && e >= 0 && e <= T, "fd_colsum_edges: bad arguments (e=%d T=%d)", e, T);
   if (e == 0) return 0;
   const int rows_per_block = 64;
@@ -221,6 +226,7 @@ int fd_colsum_edges(const uint16_t* planes, float* out, int B, int T, int N, int
 }
 
 int fd_reduce_batch(const float* in, float* out, int B, long long n, float scale, void* stream) {
+  FD_DEVICE_GUARD();
   k_reduce_batch<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(in, out, B, n, scale);
   FD_LAUNCHED();
   return 0;

@@ -231,6 +231,7 @@ size_t fd_sinegen_ws_bytes(int B, long long S) {
 int fd_sinegen_fwd(const float* f0, const float* lin_w, const float* lin_b, const float* rand_ini,
                    const float* noise, float* har, void* ws, int B, int T, int hop, int H, float sampling_rate,
                    float sine_amp, float noise_std, unsigned long long seed, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(H >= 1 && H <= SG_MAXH, "fd_sinegen_fwd: H=%d out of range", H);
   FD_REQUIRE(B > 0 && T > 0 && hop > 0, "fd_sinegen_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -250,6 +251,7 @@ int fd_sinegen_fwd(const float* f0, const float* lin_w, const float* lin_b, cons
 
 int fd_source_conv_fwd(const float* har, const float* w, const float* bias, float* out, int B, long long S, int C,
                        int k, int s, int p, void* stream) {
+  FD_DEVICE_GUARD();
   const long long S_out = (S + 2LL * p - k) / s + 1;
   FD_REQUIRE(S_out > 0, "fd_source_conv_fwd: empty output");
   const int wlen = (SC_QT - 1) * s + k;
@@ -261,6 +263,7 @@ int fd_source_conv_fwd(const float* har, const float* w, const float* bias, floa
 
 int fd_conv_post_fwd(const uint16_t* in_planes, const float* w, const float* bias, float* wav, int B, long long S,
                      int C, int k, int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(C % 8 == 0, "fd_conv_post_fwd: C=%d must be a multiple of 8", C);
   const long long n = (long long)B * S;
   long long g = (n + 255) / 256;
@@ -272,6 +275,7 @@ int fd_conv_post_fwd(const uint16_t* in_planes, const float* w, const float* bia
 }
 
 int fd_reflect_pad_split(const float* wav, uint16_t* planes, int B, long long N, int pad, int prec, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(pad < N, "fd_reflect_pad_split: pad=%d must be smaller than N=%lld", pad, N);
   const long long Np = N + 2LL * pad;
   const long long pitch = (Np + 7) / 8 * 8;

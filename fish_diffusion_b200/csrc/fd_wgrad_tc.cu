@@ -270,7 +270,6 @@ int make_plane_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, int
   return 0;
 }
 
-int g_wg_sms = 0;
 
 template <int BLOCK_N, int PREC, int NPL>
 int launch_wg(const FdWgradK& p, const uint16_t* const* row_ptr, const uint16_t* const* col_ptr, cudaStream_t stream) {
@@ -284,16 +283,13 @@ int launch_wg(const FdWgradK& p, const uint16_t* const* row_ptr, const uint16_t*
     if (rc) return rc;
   }
   auto kern = fd_wgrad_tc_kernel<BLOCK_N, PREC, NPL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[FD_MAX_DEVICES] = {false};   // the max-dynamic-smem attribute is per device
+  const int dev = fd_current_device();
+  if (!attr_set[dev]) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  if (g_wg_sms == 0) {
-    int dev = 0;
-    FD_CHECK_CUDA(cudaGetDevice(&dev));
-    FD_CHECK_CUDA(cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_wg_sms = fd_device_sms(dev);
   const int units = p.splits * p.m_tiles * p.n_tiles;
   const int grid = units < g_wg_sms ? units : g_wg_sms;
   kern<<<grid, WG_THREADS, C::SMEM_BYTES, stream>>>(tr[0], tr[1], tc[0], tc[1], p);
@@ -315,6 +311,7 @@ int launch_wg_prec(const FdWgradK& p, int prec, const uint16_t* const* row_ptr, 
 }  // namespace
 
 extern "C" int fd_wgrad_cl(const fd_wgrad_desc* d, void* stream) {
+  FD_DEVICE_GUARD();
   FD_REQUIRE(d != nullptr, "fd_wgrad_cl: null descriptor");
   FD_REQUIRE(d->B > 0 && d->T > 0 && d->splits > 0 && d->splits <= d->B, "fd_wgrad_cl: bad B=%d T=%d splits=%d", d->B,
              d->T, d->splits);

@@ -245,6 +245,7 @@ class WaveNet(nn.Module):
                   "w2t": [stat["w2t"][l] for l in range(L)], "w2t_inv": pk["w2_inv"]}
             bw["wot"], bw["wot_inv"] = pack(f32(self.output_projection.conv.weight)[:, :, 0].t().contiguous(), s_out)
             bw["wst"], bw["wst_inv"] = pack(f32(self.skip_projection.conv.weight)[:, :, 0].t().contiguous(), s_skip)
+            bw["wit"], bw["wit_inv"] = pack(f32(self.input_projection.conv.weight)[:, :, 0].t().contiguous(), s_in)
             pk["_bwd"] = bw
         self._pack, self._pack_key = pk, key
         return pk
@@ -301,13 +302,21 @@ class WaveNet(nn.Module):
         s = self.mlp[2].linear(s)
         return torch.stack([blk.diffusion_projection.linear(s) for blk in self.residual_layers], dim=1)
 
-    def forward_train_cl(self, x_cl, diffusion_step, cond_cl):
+    def forward_train_cl(self, x_cl, diffusion_step, cond_cl, x_mask=None, cond_mask=None):
         """Differentiable channels-last forward: x_cl [B,T,M], diffusion_step [B] or [1], cond_cl [B,T,E] -> eps [B,T,M].
-        Gradients flow to every parameter, to cond_cl and (through d) to the step-embedding path.  No masks: the
-        reference trains without them (diffusion.py:134)."""
+        Gradients flow to every parameter, to x_cl, to cond_cl and (through d) to the step-embedding path.  Masks
+        ([B,T] bool, True = masked) act where the reference's masked_fill calls do (wavenet.py:217-221,233-234); the
+        reference's own training passes none (diffusion.py:134).
+        Memory: the backward needs the residual stream, pre-activations and gated output of every layer as split
+        planes: L * 16 * C bytes per position (164 KB at C=512, L=20; 21 GB at B=32, T=4000) -- run inference under
+        torch.no_grad() (the registry classes' sampler does)."""
         from .wavenet_train import WaveNetTrainFn
         d = self.step_vectors(diffusion_step)
-        return WaveNetTrainFn.apply(self, x_cl.contiguous(), cond_cl.contiguous(), d, *self.train_param_list())
+        masks = None
+        if x_mask is not None or cond_mask is not None:
+            u8 = lambda m: None if m is None else m.to(device=x_cl.device, dtype=torch.uint8).contiguous()
+            masks = (u8(x_mask), u8(cond_mask))
+        return WaveNetTrainFn.apply(self, masks, x_cl.contiguous(), cond_cl.contiguous(), d, *self.train_param_list())
 
     # ------------------------------------------------------------------------------------ native forward
     @torch.no_grad()
@@ -366,10 +375,9 @@ class WaveNet(nn.Module):
         float), conditioner [B,E,T], masks [B,T] bool -> [B,M,T] (4-D in -> 4-D out)."""
         if torch.is_grad_enabled() and (x.requires_grad or conditioner.requires_grad or
                                         any(p.requires_grad for p in self.parameters())):
-            if x_masks is not None or cond_masks is not None:
-                raise NotImplementedError("the differentiable path takes no masks (the reference trains without them)")
             x3 = x[:, 0] if x.dim() == 4 else x
-            eps = self.forward_train_cl(x3.transpose(1, 2), diffusion_step, conditioner.transpose(1, 2)).transpose(1, 2)
+            eps = self.forward_train_cl(x3.transpose(1, 2), diffusion_step, conditioner.transpose(1, 2),
+                                        x_mask=x_masks, cond_mask=cond_masks).transpose(1, 2)
             return eps[:, None] if x.dim() == 4 else eps
         use_4_dim = x.dim() == 4
         if use_4_dim:

@@ -40,10 +40,13 @@ def _bwd_packs(net, pk, device):
 
 
 class WaveNetTrainFn(torch.autograd.Function):
-    """eps_cl = f(x_cl [B,T,M], cond_cl [B,T,E], d [Bs,L,C], *conv weights);  see WaveNet.train_param_list()."""
+    """eps_cl = f(x_cl [B,T,M], cond_cl [B,T,E], d [Bs,L,C], *conv weights);  see WaveNet.train_param_list().
+    `masks` = (x_mask, cond_mask) uint8 [B,T] or None each, the reference's masked_fill points (wavenet.py:217-221,
+    233-234): masked rows of relu(input_projection(x)), of the conditioner and of the output are zero; in the backward
+    that is a zeroed d_eps row, the ReLU mask of the (exactly zero) head rows, and zeroed d_cond rows."""
 
     @staticmethod
-    def forward(ctx, net, x_cl, cond_cl, d, *weights):
+    def forward(ctx, net, masks, x_cl, cond_cl, d, *weights):
         dev = x_cl.device
         N.require_cuda(x_cl, "x")
         B, T, M = x_cl.shape
@@ -55,8 +58,9 @@ class WaveNetTrainFn(torch.autograd.Function):
         i16 = dict(dtype=torch.int16, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
 
+        x_mask, cond_mask = masks if masks is not None else (None, None)
         x_planes = N.split_nwc(x_cl.detach().to(torch.float32), prec)
-        cond_planes = N.split_nwc(cond_cl.detach().to(torch.float32), prec)
+        cond_planes = N.split_nwc(cond_cl.detach().to(torch.float32), prec, mask=cond_mask)
         d = d.detach().to(torch.float32).contiguous()
         gb = torch.empty((3, L, Bs, 2 * C), **f32)
         N.check(lib.fd_wavenet_gate_bias_from_d(N.ptr(d), N.ptr(pk["w1p_f32"]), N.ptr(pk["bias_sum"]), N.ptr(gb[0]),
@@ -69,8 +73,8 @@ class WaveNetTrainFn(torch.autograd.Function):
         s_planes = torch.empty((2, B, T, C), **i16)
         h_planes = torch.empty((2, B, T, C), **i16)
         eps = torch.empty((B, T, M), **f32)
-        N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], out_planes=xs[0], w_inv_scale=pk["w_in_inv"],
-                  act=N.ACT_RELU, prec=mma, backend=backend)
+        N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], row_mask=x_mask, out_planes=xs[0],
+                  w_inv_scale=pk["w_in_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
         gb_stride = 2 * C if Bs > 1 else 0
         for l in range(L):
             flags = (1 if l == 0 else 0) | (2 if l == L - 1 else 0)
@@ -81,21 +85,31 @@ class WaveNetTrainFn(torch.autograd.Function):
                 pk["w1_inv"][l], pk["w2_inv"][l], flags, mma, backend, st), "fd_wavenet_block_fwd_train")
         N.conv_cl(s_planes, pk["w_skip"], B, T, C, C, [0], bias=pk["b_skip"], out_planes=h_planes,
                   w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
-        N.conv_cl(h_planes, pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], out_f32=eps, w_inv_scale=pk["w_out_inv"],
-                  prec=mma, backend=backend)
+        N.conv_cl(h_planes, pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], row_mask=x_mask, out_f32=eps,
+                  w_inv_scale=pk["w_out_inv"], prec=mma, backend=backend)
         ctx.net = net
+        # the packs used here are captured: a parameter update between forward and backward must not change the
+        # weights the gradients are taken at; the version key lets backward say so instead of mixing
         ctx.saved = dict(x_planes=x_planes, cond_planes=cond_planes, d=d, xs=xs, ys=ys, zs=zs, s_planes=s_planes,
-                         h_planes=h_planes, shape=(B, T, M, Bs))
+                         h_planes=h_planes, shape=(B, T, M, Bs), x_mask=x_mask, cond_mask=cond_mask,
+                         pack_key=net._pack_key)
         ctx.need_cond = cond_cl.requires_grad
+        ctx.need_x = x_cl.requires_grad
         return eps
 
     @staticmethod
     def backward(ctx, d_eps):
         net, sv = ctx.net, ctx.saved
+        if sv is None:
+            raise RuntimeError("WaveNetTrainFn: backward ran twice (retain_graph is not supported: the saved "
+                               "activations -- ~3 GB per 20k positions -- are released after the first backward)")
         B, T, M, Bs = sv["shape"]
         C, E, L = net.residual_channels, net.d_encoder, net.n_layers
         dev = d_eps.device
         pk = net._packed(dev, want_bwd=True)
+        if net._pack_key != sv["pack_key"]:
+            raise RuntimeError("WaveNetTrainFn: a parameter of the denoiser changed between forward and backward "
+                               "(optimizer / EMA step or load_state_dict in between); run backward first")
         bw = _bwd_packs(net, pk, dev)
         prec, mma, pref = pk["prec"], pk["mma"], pk["backend"]
         perm, gate_tile = pk["perm"], pk["gate_tile"]
@@ -164,6 +178,8 @@ class WaveNetTrainFn(torch.autograd.Function):
 
         # ---------------------------------------------------------------- tail (wavenet.py:229-231)
         de = d_eps.detach().to(torch.float32).contiguous()
+        if sv["x_mask"] is not None:
+            de = de.masked_fill(sv["x_mask"].bool()[:, :, None], 0.0)
         de_planes = N.split_nwc(de, prec, scale=S)
         if direct:
             grads["output_projection.w"] = wgrad_direct([de_planes], [(0, 0, M)], [sv["h_planes"]], [(0, 0, 0, C)])
@@ -296,8 +312,14 @@ class WaveNetTrainFn(torch.autograd.Function):
         else:
             grads["input_projection.w"] = wgrad(fold(dx0m, C), C, fold(sv["x_planes"], M), M)
         grads["input_projection.b"] = colsum(planes=dx0m, Nn=C).sum(0)
+        d_x = None
+        if ctx.need_x:     # d(x) = d(x_0 masked by the ReLU) . W_in   (wavenet.py:211)
+            d_x = torch.empty((B, T, M), **f32)
+            dgrad(dx0m, C, bw["wit"], bw["wit_inv"] * inv_S, M, C, [(0, 0, 0, C)], out_f32=d_x)
+        if d_cond is not None and sv["cond_mask"] is not None:
+            d_cond = d_cond.masked_fill(sv["cond_mask"].bool()[:, :, None], 0.0)
 
-        out = [None, None, d_cond, d_d]
+        out = [None, None, d_x, d_cond, d_d]
         for kind, key in net.train_param_keys():
             gr = grads[key]
             if kind == "w1x1":

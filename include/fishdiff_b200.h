@@ -37,6 +37,12 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------- misc */
 int fd_abi_version(void);
 const char* fd_last_error(void);
+/* Device the caller's buffers live on (thread-local; -1 = "whatever is current", the default).  Every entry point
+ * makes it the current CUDA device for the duration of the call and restores the caller's device afterwards, so a
+ * module on cuda:N works without torch.cuda.set_device (the reference relies on PyTorch's per-tensor device
+ * dispatch for the same thing, e.g. `model.to(device)` in tools/diffusion/inference.py:57-60).  Per-device state
+ * (SM count, dynamic shared-memory attributes) is cached per device. */
+void fd_set_device(int device);
 /* number of kernel launches issued by this library since process start (bench.py "gpu_launches") */
 long long fd_launch_count(void);
 /* per-launch device timing of the tap-GEMM kernels (CUDA events on the launching stream), used by bench.py for
