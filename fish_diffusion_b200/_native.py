@@ -52,6 +52,17 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class ResPairDesc(ctypes.Structure):
+    """struct fd_respair_desc (include/fishdiff_b200.h)."""
+    _fields_ = [
+        ("in_planes", c_void_p), ("w1", c_void_p), ("w2", c_void_p), ("b1", c_void_p), ("b2", c_void_p),
+        ("out_planes", c_void_p), ("out_f32", c_void_p),
+        ("B", c_int), ("T", c_int), ("C", c_int), ("k1", c_int), ("d1", c_int), ("k2", c_int),
+        ("w1_inv_scale", c_float), ("w2_inv_scale", c_float), ("in_slope", c_float), ("out_slope", c_float),
+        ("planes_scale", c_float), ("out_accum", c_int), ("prec", c_int),
+    ]
+
+
 class WgradDesc(ctypes.Structure):
     """struct fd_wgrad_desc (include/fishdiff_b200.h)."""
     _fields_ = [
@@ -86,6 +97,7 @@ _SIGS = {
     "fd_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_longlong), c_int]),
     "fd_split_ncw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fd_split_nwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "fd_lrelu_split": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_float, c_int, c_void_p]),
     "fd_transpose_nwc_to_ncw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fd_transpose_ncw_to_nwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fd_pack_weight": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_int, c_void_p]),
@@ -94,6 +106,8 @@ _SIGS = {
     "fd_wavenet_block_fwd": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 +
                              [c_float, c_float, c_int, c_int, c_int, c_void_p]),
     "fd_conv_cl_fwd": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "fd_respair_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "fd_respair_fwd": (c_int, [POINTER(ResPairDesc), c_void_p]),
     "fd_ddpm_step": (c_int, [c_void_p] * 5 + [c_longlong] + [c_float] * 7 + [c_ulonglong, c_ulonglong, c_ulonglong, c_int,
                                                                                c_void_p]),
     "fd_lincomb": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p]),
@@ -257,6 +271,23 @@ def conv_cl(in_planes, w_planes, B, T, Cin, N, shifts, *, bias=None, addend=None
     d.w_inv_scale, d.post_scale, d.planes_scale, d.act_slope = w_inv_scale, post_scale, planes_scale, act_slope
     d.out_accum, d.act, d.prec, d.backend = int(out_accum), act, prec, backend
     check(lib().fd_conv_cl_fwd(ctypes.byref(d), stream_ptr(in_planes.device)), "fd_conv_cl_fwd")
+
+
+def respair_supported(C: int, k1: int, d1: int, k2: int) -> bool:
+    return bool(lib().fd_respair_supported(C, k1, d1, k2))
+
+
+def respair(in_planes, w1, w2, b1, b2, B, T, C, k1, d1, k2, *, out_planes=None, out_f32=None, out_accum=False,
+            w1_inv_scale=1.0, w2_inv_scale=1.0, in_slope=0.1, out_slope=0.1, planes_scale=1.0, prec=PREC_F16):
+    """Fused ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) on planes of lrelu(x) (fd_respair_fwd)."""
+    d = ResPairDesc()
+    d.in_planes, d.w1, d.w2, d.b1, d.b2 = ptr(in_planes), ptr(w1), ptr(w2), ptr(b1), ptr(b2)
+    d.out_planes, d.out_f32 = ptr(out_planes), ptr(out_f32)
+    d.B, d.T, d.C, d.k1, d.d1, d.k2 = B, T, C, k1, d1, k2
+    d.w1_inv_scale, d.w2_inv_scale = w1_inv_scale, w2_inv_scale
+    d.in_slope, d.out_slope, d.planes_scale = in_slope, out_slope, planes_scale
+    d.out_accum, d.prec = int(out_accum), prec
+    check(lib().fd_respair_fwd(ctypes.byref(d), stream_ptr(in_planes.device)), "fd_respair_fwd")
 
 
 PROF_KINDS = {0: "linear/tc", 1: "linear/simt", 2: "gate/tc", 3: "gate/simt", 4: "res_skip/tc", 5: "res_skip/simt",

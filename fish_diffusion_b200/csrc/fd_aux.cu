@@ -49,6 +49,22 @@ __global__ void k_split_nwc(const float* __restrict__ src, const uint8_t* __rest
   }
 }
 
+// planes = split(lrelu(src * scale, slope)): the multi-receptive-field average + LeakyReLU that feeds the next
+// upsampling stage (models.py:420,432)
+__global__ void k_lrelu_split(const float* __restrict__ src, uint16_t* __restrict__ planes, long long n, float scale,
+                              float slope, int prec) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    float v[4];
+    fd_load_f32<4>(src + e, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = fd_act(v[k] * scale, slope);
+    fd_store_planes<4>(planes, (size_t)n, (size_t)e, v, prec);
+  }
+}
+
 // generic 2-D transpose of the two inner dims: src [B][R][S] -> dst [B][S][R]
 __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int R, int S) {
   __shared__ float tile[32][33];
@@ -377,6 +393,14 @@ int fd_split_nwc(const float* src, const uint8_t* mask, uint16_t* planes, int B,
   FD_REQUIRE(C % 4 == 0, "fd_split_nwc: C=%d must be a multiple of 4", C);
   const long long rows = (long long)B * T;
   k_split_nwc<<<grid_for(rows * C / 4), 256, 0, (cudaStream_t)stream>>>(src, mask, planes, rows, C, scale, prec);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_lrelu_split(const float* src, uint16_t* planes, long long n, float scale, float slope, int prec, void* stream) {
+  FD_DEVICE_GUARD();
+  FD_REQUIRE(n % 4 == 0, "fd_lrelu_split: n=%lld must be a multiple of 4", n);
+  k_lrelu_split<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(src, planes, n, scale, slope, prec);
   FD_LAUNCHED();
   return 0;
 }

@@ -1,0 +1,558 @@
+// Fused NSF-HiFiGAN ResBlock1 pair on tcgen05 (sm_100a):
+//
+//     x' = x + c2( lrelu( c1( lrelu(x) ) ) )          (reference models.py:103-110, one iteration of the loop)
+//
+// in ONE kernel per (c1, c2) pair.  HBM traffic per element: 4 bytes in (split planes of lrelu(x)) + 4 bytes out,
+// against 24 for the two separate tap-GEMM launches with an fp32 residual master.
+//
+//   * the activation tile is loaded ONCE with its halo (128 + (k1-1)*d1 rows, one TMA box per 64-channel block, hi
+//     and lo planes in the same box); every conv tap is the SAME shared-memory tile addressed through a tcgen05
+//     descriptor whose start address is advanced by whole rows (tests/native/desc_shift_probe.cu: the tensor core
+//     swizzles on absolute shared-memory address bits, so any row offset of a TMA-written tile is addressable);
+//   * c1's output never leaves the SM: the epilogue warps read the accumulator from TMEM, apply bias + LeakyReLU,
+//     split into hi/lo planes and write them into a second swizzled shared-memory tile that is c2's A operand;
+//   * the residual x is recovered from the input tile (LeakyReLU is invertible) and pre-loaded, with c2's bias, into
+//     c2's TMEM accumulator by tcgen05.st, so GEMM2 accumulates on top of it and the input tile is free for the next
+//     tile's TMA load while GEMM2 runs;
+//   * three split products per k16 step cost TWO tensor-core instructions: a_hi x [w_hi | w_lo] (the hi and lo weight
+//     planes are adjacent rows of one shared-memory tile = one B operand of 2C columns) and a_lo x w_hi; the two
+//     accumulator halves are summed in the epilogue.  That cuts the shared-memory operand traffic, which is what
+//     bounds narrow-N tcgen05 shapes;
+//   * the output goes through a swizzled staging tile and TMA: plane stores, or fp32 store / reduce-add for the
+//     multi-receptive-field sum (models.py:426-432).
+//
+// Warp roles (persistent, one CTA per SM): 0 = weight TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 3 = activation-tile TMA producer, 4.. = epilogue (8 warps; 4 at C = 16).
+#include <cuda.h>
+#include <cstring>
+#include "fd_common.cuh"
+#include "fd_host.h"
+#include "fd_tc_ptx.cuh"
+
+namespace {
+
+constexpr int RP_MID_ROWS = 144;   // 128 rows of c1 output + 16 zero rows read by the trailing taps of c2
+constexpr int RP_RIN_MAX = 184;    // 128 + (k1-1)*d1 rounded up to 8, largest supported halo (k=11, d=5)
+
+struct FdResPairK {
+  int B, T;
+  int k1, d1, k2;
+  int h1, h2;        // halos of c1 / c2 in rows
+  int r_in, r_out;   // rows of the input box (multiple of 8) / valid output rows per tile
+  int single;        // one product (hi planes only)
+  int mode;          // 0: planes out, 1: fp32 store, 2: fp32 reduce-add
+  float inv_s1, inv_s2, s2;
+  float in_slope_inv, out_slope, planes_scale;
+  const float* b1;
+  const float* b2;
+};
+
+template <int C>
+struct RpCfg {
+  static constexpr int BK_A = C >= 64 ? 64 : C;          // channels per shared-memory activation block
+  static constexpr int NKB = C / BK_A;
+  static constexpr int ROWB = BK_A * 2;                   // bytes per activation row
+  static constexpr uint32_t SWZ_A = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;
+  static constexpr uint32_t LT_A = ROWB == 128 ? 2u : ROWB == 64 ? 4u : 6u;
+  static constexpr int BKW = C == 128 ? 32 : BK_A;        // K extent of one weight unit
+  static constexpr int WROWB = BKW * 2;
+  static constexpr uint32_t LT_W = WROWB == 128 ? 2u : WROWB == 64 ? 4u : 6u;
+  static constexpr int UNIT_BYTES = 2 * C * WROWB;        // [2 planes][C rows][BKW]
+  static constexpr int UNITS_PER_TAP = C / BKW;
+  static constexpr int GROUP_RAW = 16384 / UNIT_BYTES;
+  static constexpr int GROUP = GROUP_RAW > 8 ? 8 : GROUP_RAW;   // weight units per pipeline stage
+  static constexpr int STAGE_BYTES = GROUP * UNIT_BYTES;
+  static constexpr int IN_KB_BYTES = 2 * RP_RIN_MAX * ROWB;
+  static constexpr int IN_BYTES = NKB * IN_KB_BYTES;
+  static constexpr int MID_PLANE_BYTES = RP_MID_ROWS * ROWB;
+  static constexpr int MID_KB_BYTES = 2 * MID_PLANE_BYTES;
+  static constexpr int MID_BYTES = NKB * MID_KB_BYTES;     // also the output staging (>= 128 * C * 4 bytes of fp32)
+  static constexpr int EPI_WARPS = C >= 32 ? 8 : 4;
+  static constexpr int HALVES = EPI_WARPS / 4;
+  static constexpr int COLS = C / HALVES;                   // columns per epilogue thread
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 128 + EPI_THREADS;
+  static constexpr int TMEM_COLS = 4 * C < 32 ? 32 : 4 * C;  // acc1 [0,2C) | acc2 [2C,4C)
+  static constexpr int FB = C >= 32 ? 32 : C;               // fp32 staging: floats per box row
+  static constexpr int FROWB = FB * 4;
+  static constexpr uint32_t SWZ_F = FROWB == 128 ? 7u : 3u;
+  static constexpr int NFB = C / FB;
+  static constexpr int FBOX_BYTES = 128 * FROWB;
+  static constexpr int FIXED = 1024 + IN_BYTES + MID_BYTES + 2 * C * 4 + 256;
+  static constexpr int RAW_STAGES = (227 * 1024 - FIXED) / STAGE_BYTES;
+  static constexpr int NUM_STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = FIXED + NUM_STAGES * STAGE_BYTES;
+  static_assert(NUM_STAGES >= 2, "weight ring needs two stages");
+  static_assert(NFB * FBOX_BYTES <= MID_BYTES, "fp32 staging must fit the mid tile");
+};
+
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(&v[0]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int C, int PREC>
+__global__ void __launch_bounds__((RpCfg<C>::THREADS), 1)
+fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
+                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
+                     const FdResPairK p) {
+  using K = RpCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* in_s = smem;
+  uint8_t* mid_s = in_s + K::IN_BYTES;
+  uint8_t* w_s = mid_s + K::MID_BYTES;
+  float* bias_s = reinterpret_cast<float*>(w_s + K::NUM_STAGES * K::STAGE_BYTES);   // b1 [C] | b2 [C]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(bias_s + 2 * C);
+  uint64_t* w_empty = w_full + K::NUM_STAGES;
+  uint64_t* in_full = w_empty + K::NUM_STAGES;
+  uint64_t* in_empty = in_full + 1;
+  uint64_t* acc1_full = in_empty + 1;
+  uint64_t* mid_ready = acc1_full + 1;
+  uint64_t* acc2_full = mid_ready + 1;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc2_full + 1);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int tiles_t = (p.T + p.r_out - 1) / p.r_out;
+  const int num_tiles = p.B * tiles_t;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_in); prefetch_tmap(&tm_w1); prefetch_tmap(&tm_w2); prefetch_tmap(&tm_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < K::NUM_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(in_full, 1); mbar_init(in_empty, K::EPI_WARPS);
+    mbar_init(acc1_full, 1); mbar_init(mid_ready, K::EPI_WARPS); mbar_init(acc2_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                 "r"((uint32_t)K::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // biases; the 16 trailing rows of the mid tile are zero for the whole kernel
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { bias_s[i] = p.b1[i]; bias_s[C + i] = p.b2[i]; }
+  for (int i = threadIdx.x; i < K::NKB * 2 * K::ROWB; i += blockDim.x)      // 16 rows = ROWB 16-byte chunks per plane
+    *reinterpret_cast<uint4*>(mid_s + (i / K::ROWB) * K::MID_PLANE_BYTES + 128 * K::ROWB + (i % K::ROWB) * 16) =
+        make_uint4(0, 0, 0, 0);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 2 * C;
+
+  const int units1 = p.k1 * K::UNITS_PER_TAP, units2 = p.k2 * K::UNITS_PER_TAP;
+
+  if (warp == 0) {
+    // =========================================================== weight producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const CUtensorMap* tm = g2 == 0 ? &tm_w1 : &tm_w2;
+          const int units = g2 == 0 ? units1 : units2;
+          for (int u0 = 0; u0 < units; u0 += K::GROUP) {
+            const int nb = min(K::GROUP, units - u0);
+            mbar_wait(&w_empty[stage], phase ^ 1);
+            mbar_expect_tx(&w_full[stage], nb * K::UNIT_BYTES);
+            uint8_t* slot = w_s + stage * K::STAGE_BYTES;
+            for (int g = 0; g < nb; ++g) {
+              const int u = u0 + g;
+              const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
+              tma_load_3d(slot + g * K::UNIT_BYTES, tm, &w_full[stage], tap * C + kw * K::BKW, 0, 0);
+            }
+            if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // =========================================================== activation-tile producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * p.r_out;
+        mbar_wait(in_empty, (it & 1) ^ 1);
+        mbar_expect_tx(in_full, K::NKB * 2 * p.r_in * K::ROWB);
+        for (int kb = 0; kb < K::NKB; ++kb)
+          tma_load_4d(in_s + kb * K::IN_KB_BYTES, &tm_in, in_full, kb * K::BK_A, t0 - p.h2 - p.h1, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t fmt = PREC == FD_F16 ? 0u : 1u;
+      const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_2c = idesc_base | ((uint32_t)((2 * C) >> 3) << 17);
+      const uint32_t idesc_c = idesc_base | ((uint32_t)(C >> 3) << 17);
+      constexpr uint32_t SBO_A = 8 * K::ROWB, SBO_W = 8 * K::WROWB;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const int units = g2 == 0 ? units1 : units2;
+          const uint32_t d_tmem = g2 == 0 ? acc1 : acc2;
+          const uint32_t a_base = g2 == 0 ? smem_u32(in_s) : smem_u32(mid_s);
+          const uint32_t a_kb = g2 == 0 ? K::IN_KB_BYTES : K::MID_KB_BYTES;
+          const uint32_t a_plane = g2 == 0 ? (uint32_t)p.r_in * K::ROWB : (uint32_t)K::MID_PLANE_BYTES;
+          const int dil = g2 == 0 ? p.d1 : 1;
+          if (g2 == 0) mbar_wait(in_full, it & 1); else mbar_wait(mid_ready, it & 1);
+          tc_fence_after();
+          for (int u0 = 0; u0 < units; u0 += K::GROUP) {
+            const int nb = min(K::GROUP, units - u0);
+            mbar_wait(&w_full[stage], phase);
+            tc_fence_after();
+            for (int g = 0; g < nb; ++g) {
+              const int u = u0 + g;
+              const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
+              const int ch = kw * K::BKW;
+              const uint32_t a_hi = a_base + (ch / K::BK_A) * a_kb + (uint32_t)(tap * dil) * K::ROWB + (ch % K::BK_A) * 2;
+              const uint32_t w_addr = smem_u32(w_s + stage * K::STAGE_BYTES + g * K::UNIT_BYTES);
+#pragma unroll
+              for (int k = 0; k < K::BKW / 16; ++k) {
+                const uint64_t da_hi = make_kmajor_desc(a_hi + k * 32, SBO_A, K::LT_A);
+                const uint64_t dw = make_kmajor_desc(w_addr + k * 32, SBO_W, K::LT_W);
+                const uint32_t accum = (g2 == 1 || u != 0 || k != 0) ? 1u : 0u;
+                if (!p.single) {
+                  const uint64_t da_lo = make_kmajor_desc(a_hi + a_plane + k * 32, SBO_A, K::LT_A);
+                  umma_f16(d_tmem, da_hi, dw, idesc_2c, accum);     // a_hi x [w_hi | w_lo] -> columns [0,2C)
+                  umma_f16(d_tmem, da_lo, dw, idesc_c, 1u);         // a_lo x w_hi         -> columns [0,C)
+                } else {
+                  umma_f16(d_tmem, da_hi, dw, idesc_c, accum);
+                }
+              }
+            }
+            umma_commit(&w_empty[stage]);
+            if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(g2 == 0 ? acc1_full : acc2_full);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================================================== epilogue
+    const int q = warp % 4;
+    const int half = (warp - 4) / 4;
+    const int row = q * 32 + lane;
+    const int col_base = half * K::COLS;
+    const int etid = threadIdx.x - 128;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t in_u = smem_u32(in_s), mid_u = smem_u32(mid_s);
+    const float slope_mid = 0.1f;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / tiles_t, t0 = (tile % tiles_t) * p.r_out;
+      // ---- phase 1: GEMM1 done
+      mbar_wait(acc1_full, it & 1);
+      tc_fence_after();
+      mbar_wait(in_full, it & 1);                    // visibility of the TMA-written input tile to these threads
+      // the staging tile (= mid tile) of the previous output must have been read by its TMA stores
+      if (etid == 0) bulk_wait_read0();
+      asm volatile("bar.sync 1, %0;" ::"r"(K::EPI_THREADS) : "memory");
+      if (p.mode != 0) {   // the fp32 staging image overlaps the zero rows of the mid tile: restore them
+        for (int i = etid; i < K::NKB * 2 * K::ROWB; i += K::EPI_THREADS)
+          *reinterpret_cast<uint4*>(mid_s + (i / K::ROWB) * K::MID_PLANE_BYTES + 128 * K::ROWB + (i % K::ROWB) * 16) =
+              make_uint4(0, 0, 0, 0);
+      }
+      // (a) residual + c2 bias -> accumulator 2 (pre-scaled by the weight prescale of c2), zeros in the [w_lo] half
+      {
+        const int n = row + p.h1 + p.h2;
+        const uint32_t lo_off = (uint32_t)p.r_in * K::ROWB;
+#pragma unroll
+        for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+          const int col = col_base + c16 * 16;
+          const int kb = col / K::BK_A, cc = col % K::BK_A;
+          const uint32_t base = in_u + kb * K::IN_KB_BYTES;
+          float v[16];
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const uint32_t off = swz((uint32_t)n * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+            const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + lo_off + off);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a0, a1;
+              fd_combine2(hw[j], lw[j], PREC, a0, a1);
+              a0 = a0 >= 0.f ? a0 : a0 * p.in_slope_inv;
+              a1 = a1 >= 0.f ? a1 : a1 * p.in_slope_inv;
+              v[hq * 8 + 2 * j] = (a0 + bias_s[C + col + hq * 8 + 2 * j]) * p.s2;
+              v[hq * 8 + 2 * j + 1] = (a1 + bias_s[C + col + hq * 8 + 2 * j + 1]) * p.s2;
+            }
+          }
+          tmem_st16(acc2 + lane_addr + col, v);
+          if (!p.single) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            tmem_st16(acc2 + lane_addr + C + col, v);
+          }
+        }
+        tmem_st_wait();
+      }
+      // (b) accumulator 1 -> bias, LeakyReLU, zero outside [0,T), split planes -> mid tile (c2's A operand)
+      {
+        const int t = t0 - p.h2 + row;
+        const bool ok = t >= 0 && t < p.T;
+#pragma unroll
+        for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+          const int col = col_base + c16 * 16;
+          float a[16], a2[16];
+          tmem_ld16_nowait(acc1 + lane_addr + col, a);
+          if (!p.single) tmem_ld16_nowait(acc1 + lane_addr + C + col, a2);
+          tmem_wait16(a);
+          if (!p.single) {
+            tmem_wait16(a2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] += a2[i];
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y0 = a[2 * j] * p.inv_s1 + bias_s[col + 2 * j];
+            float y1 = a[2 * j + 1] * p.inv_s1 + bias_s[col + 2 * j + 1];
+            y0 = ok ? fd_act(y0, slope_mid) : 0.f;
+            y1 = ok ? fd_act(y1, slope_mid) : 0.f;
+            fd_split2(y0, y1, PREC, hi[j], lo[j]);
+          }
+          const int kb = col / K::BK_A, cc = col % K::BK_A;
+          const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const uint32_t off = swz((uint32_t)row * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+            sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
+            sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(mid_ready); mbar_arrive(in_empty); }
+
+      // ---- phase 2: GEMM2 done (accumulator 2 = (x + b2) * s2 + conv products)
+      mbar_wait(acc2_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+        const int col = col_base + c16 * 16;
+        float a[16], a2[16];
+        tmem_ld16_nowait(acc2 + lane_addr + col, a);
+        if (!p.single) tmem_ld16_nowait(acc2 + lane_addr + C + col, a2);
+        tmem_wait16(a);
+        if (!p.single) {
+          tmem_wait16(a2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] += a2[i];
+        }
+        if (p.mode == 0) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            fd_split2(fd_act(a[2 * j] * p.inv_s2, p.out_slope) * p.planes_scale,
+                      fd_act(a[2 * j + 1] * p.inv_s2, p.out_slope) * p.planes_scale, PREC, hi[j], lo[j]);
+          const int kb = col / K::BK_A, cc = col % K::BK_A;
+          const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const uint32_t off = swz((uint32_t)row * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+            sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
+            sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
+          }
+        } else {
+          const int fbx = col / K::FB, cc = col % K::FB;
+          const uint32_t base = mid_u + fbx * K::FBOX_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = swz((uint32_t)row * K::FROWB + (uint32_t)(cc / 4 + j) * 16, K::SWZ_F);
+            sts_u4(base + off, __float_as_uint(a[4 * j] * p.inv_s2), __float_as_uint(a[4 * j + 1] * p.inv_s2),
+                   __float_as_uint(a[4 * j + 2] * p.inv_s2), __float_as_uint(a[4 * j + 3] * p.inv_s2));
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"r"(K::EPI_THREADS) : "memory");
+      if (etid == 0) {
+        if (p.mode == 0) {
+          for (int kb = 0; kb < K::NKB; ++kb)
+            for (int pl = 0; pl < 2; ++pl)
+              tma_store_4d(&tm_out, mid_u + kb * K::MID_KB_BYTES + pl * K::MID_PLANE_BYTES, kb * K::BK_A, t0, b, pl);
+        } else {
+          for (int fbx = 0; fbx < K::NFB; ++fbx) {
+            if (p.mode == 1) tma_store_3d(&tm_out, mid_u + fbx * K::FBOX_BYTES, fbx * K::FB, t0, b);
+            else tma_reduce_add_3d(&tm_out, mid_u + fbx * K::FBOX_BYTES, fbx * K::FB, t0, b);
+          }
+        }
+        bulk_commit();
+      }
+    }
+    if (etid == 0) bulk_wait0();
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+CUtensorMapSwizzle swizzle_for_bytes(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                         : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// planes [2][B][T][C] (uint16): box {bk, rows, 1, nplanes}
+int make_planes_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, int bk, int rows, int nplanes) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2, (cuuint64_t)B * T * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)rows, 1, (cuuint32_t)nplanes};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(bk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(planes) failed: %d (B=%d T=%d C=%d bk=%d rows=%d)", (int)r, B, T,
+             C, bk, rows);
+  return 0;
+}
+
+int make_f32_map(CUtensorMap* m, const float* ptr, int B, int T, int C, int fb, int rows) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)fb, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(fb * 4), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed: %d (B=%d T=%d C=%d)", (int)r, B, T, C);
+  return 0;
+}
+
+// packed weights [2][C][K] (uint16): box {bkw, C, 2}
+int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)C, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)Ktot * 2, (cuuint64_t)C * Ktot * 2};
+  cuuint32_t box[3] = {(cuuint32_t)bkw, (cuuint32_t)C, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(bkw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(w pair) failed: %d (C=%d K=%d)", (int)r, C, Ktot);
+  return 0;
+}
+
+template <int C, int PREC>
+int launch_respair(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t stream) {
+  using K = RpCfg<C>;
+  CUtensorMap tin, tw1, tw2, tout;
+  int rc = make_planes_map(&tin, d.in_planes, p.B, p.T, C, K::BK_A, p.r_in, 2);
+  if (rc) return rc;
+  rc = make_wpair_map(&tw1, d.w1, C, p.k1 * C, K::BKW);
+  if (rc) return rc;
+  rc = make_wpair_map(&tw2, d.w2, C, p.k2 * C, K::BKW);
+  if (rc) return rc;
+  if (p.mode == 0) rc = make_planes_map(&tout, d.out_planes, p.B, p.T, C, K::BK_A, p.r_out, 1);
+  else rc = make_f32_map(&tout, d.out_f32, p.B, p.T, C, K::FB, p.r_out);
+  if (rc) return rc;
+  auto kern = fd_respair_tc_kernel<C, PREC>;
+  static bool attr_set[FD_MAX_DEVICES] = {false};
+  const int dev = fd_current_device();
+  if (!attr_set[dev]) {
+    FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  const int tiles = p.B * ((p.T + p.r_out - 1) / p.r_out);
+  const int sms = fd_device_sms(dev);
+  kern<<<tiles < sms ? tiles : sms, K::THREADS, K::SMEM_BYTES, stream>>>(tin, tw1, tw2, tout, p);
+  FD_CHECK_CUDA(cudaGetLastError());
+  fd_count_launch(1);
+  return 0;
+}
+
+template <int C>
+int launch_respair_prec(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t stream) {
+  return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16>(d, p, stream) : launch_respair<C, FD_BF16>(d, p, stream);
+}
+
+}  // namespace
+
+extern "C" int fd_respair_supported(int C, int k1, int d1, int k2) {
+  if (C != 16 && C != 32 && C != 64 && C != 128) return 0;
+  if (k1 < 1 || k2 < 1 || (k1 & 1) == 0 || (k2 & 1) == 0 || d1 < 1) return 0;
+  if (k2 - 1 > RP_MID_ROWS - 128) return 0;
+  if (128 + (k1 - 1) * d1 > RP_RIN_MAX) return 0;
+  if ((k2 - 1) / 2 > (k1 - 1) / 2 * d1) return 0;       // the residual rows must lie inside the input tile
+  return 1;
+}
+
+extern "C" int fd_respair_fwd(const fd_respair_desc* d, void* stream) {
+  FD_DEVICE_GUARD();
+  FD_REQUIRE(d != nullptr, "fd_respair_fwd: null descriptor");
+  FD_REQUIRE(fd_respair_supported(d->C, d->k1, d->d1, d->k2), "fd_respair_fwd: unsupported shape C=%d k1=%d d1=%d k2=%d",
+             d->C, d->k1, d->d1, d->k2);
+  FD_REQUIRE(d->B > 0 && d->T > 0, "fd_respair_fwd: bad shape B=%d T=%d", d->B, d->T);
+  FD_REQUIRE(d->in_planes && d->w1 && d->w2 && d->b1 && d->b2, "fd_respair_fwd: null pointer");
+  FD_REQUIRE((d->out_planes != nullptr) != (d->out_f32 != nullptr), "fd_respair_fwd: exactly one of out_planes / out_f32");
+  FD_REQUIRE(d->in_slope > 0.f, "fd_respair_fwd: the input LeakyReLU slope must be positive (it is inverted)");
+  FD_REQUIRE((const void*)d->out_planes != (const void*)d->in_planes, "fd_respair_fwd: in-place is not supported (halo reads)");
+  FdResPairK p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.T = d->T; p.k1 = d->k1; p.d1 = d->d1; p.k2 = d->k2;
+  p.h1 = (d->k1 - 1) / 2 * d->d1; p.h2 = (d->k2 - 1) / 2;
+  p.r_in = (128 + (d->k1 - 1) * d->d1 + 7) / 8 * 8;
+  p.r_out = 128 - (d->k2 - 1);
+  p.single = (d->prec & FD_SINGLE) ? 1 : 0;
+  p.mode = d->out_planes != nullptr ? 0 : (d->out_accum ? 2 : 1);
+  p.inv_s1 = d->w1_inv_scale; p.inv_s2 = d->w2_inv_scale; p.s2 = 1.f / d->w2_inv_scale;
+  p.in_slope_inv = 1.f / d->in_slope; p.out_slope = d->out_slope; p.planes_scale = d->planes_scale;
+  p.b1 = d->b1; p.b2 = d->b2;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->C) {
+    case 128: return launch_respair_prec<128>(*d, p, st);
+    case 64: return launch_respair_prec<64>(*d, p, st);
+    case 32: return launch_respair_prec<32>(*d, p, st);
+    default: return launch_respair_prec<16>(*d, p, st);
+  }
+}

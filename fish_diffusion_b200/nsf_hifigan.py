@@ -160,6 +160,9 @@ class Generator(nn.Module):
         self.conv_post.apply(init_weights)
         self.precision = precision
         self.backend = os.environ.get("FD_BACKEND", backend)
+        # fused ResBlock pairs (csrc/fd_respair_tc.cu): c1 -> lrelu -> c2 -> +x in one kernel, residual stream kept
+        # as split planes only.  FD_VOC_FUSED=0 selects the conv-by-conv path (the SIMT back end always uses it).
+        self.fused = os.environ.get("FD_VOC_FUSED", "1") != "0"
         self._pack = None
         self._pack_key = None
 
@@ -203,7 +206,7 @@ class Generator(nn.Module):
         s = N.pow2_scale(w2)
         bias = conv.bias.detach().to(device=device, dtype=torch.float32).contiguous()
         offs = [(j - (K - 1) // 2) * d for j in range(K)]
-        pc = dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, Ci=Ci, N=Co, shifts=offs, bias=bias,
+        pc = dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, Ci=Ci, N=Co, shifts=offs, bias=bias, K=K, d=d,
                   backend=self._backend_for(Co, Ci, K))
         F = self._fold_factor(Ci, Co, K, d)
         if F > 1 and pc["backend"] == N.BACKEND_TC:
@@ -270,6 +273,49 @@ class Generator(nn.Module):
         N.conv_cl(in_planes, pc["w"], B, T, pc["Ci"], pc["N"], pc["shifts"], bias=pc["bias"], w_inv_scale=pc["inv"],
                   prec=self._pack["mma"], backend=pc["backend"], **kw)
 
+    def _stage_fused(self, pk, i, Co) -> bool:
+        """All three ResBlocks of stage i can run as fused pairs (tensor-core back end, ResBlock1, supported shapes)."""
+        if not self.fused or self.backend == "simt":
+            return False
+        nk = self.num_kernels
+        for j in range(nk):
+            rb = pk["res"][i * nk + j]
+            if rb["kind"] != 1:
+                return False
+            for c1, c2 in zip(rb["c1"], rb["c2"]):
+                if c1["backend"] != N.BACKEND_TC or not N.respair_supported(Co, c1["K"], c1["d"], c2["K"]) or c2["d"] != 1:
+                    return False
+        return True
+
+    def _stage_fused_run(self, pk, i, PA, B, Lo, Co, out_slope):
+        """MRF stage (models.py:426-432) on fused pairs.  PA = planes of lrelu(x, 0.1).  Each ResBlock chain runs
+        pair by pair on plane buffers (4 B/element in, 4 B/element out); the last pair of a chain adds its fp32 result
+        into XS by TMA reduce-add; one elementwise pass makes the next stage's input lrelu(XS / num_kernels)."""
+        dev = PA.device
+        nk = self.num_kernels
+        mma = pk["mma"]
+        XS = torch.empty((B, Lo, Co), dtype=torch.float32, device=dev)
+        bufs = [torch.empty_like(PA), torch.empty_like(PA)]
+        for j in range(nk):
+            rb = pk["res"][i * nk + j]
+            n = len(rb["c1"])
+            src = PA
+            for m in range(n):
+                c1, c2 = rb["c1"][m], rb["c2"][m]
+                kw = dict(w1_inv_scale=c1["inv"], w2_inv_scale=c2["inv"], in_slope=LRELU_SLOPE, prec=mma)
+                if m < n - 1:
+                    dst = bufs[m % 2]
+                    N.respair(src, c1["w"], c2["w"], c1["bias"], c2["bias"], B, Lo, Co, c1["K"], c1["d"], c2["K"],
+                              out_planes=dst, out_slope=LRELU_SLOPE, **kw)
+                    src = dst
+                else:
+                    N.respair(src, c1["w"], c2["w"], c1["bias"], c2["bias"], B, Lo, Co, c1["K"], c1["d"], c2["K"],
+                              out_f32=XS, out_accum=j > 0, **kw)
+        nxt = torch.empty_like(PA)
+        N.check(N.lib().fd_lrelu_split(N.ptr(XS), N.ptr(nxt), XS.numel(), 1.0 / nk, out_slope, pk["prec"],
+                                       N.stream_ptr(dev)), "fd_lrelu_split")
+        return nxt
+
     @torch.no_grad()
     def source(self, f0, S_hop, rand_ini=None, sine_noise=None, seed=None):
         """f0 [B,T] -> harmonic excitation [B, T*hop] (models.py:411-415).  rand_ini [B,9] / sine_noise [B,S,9] may
@@ -329,11 +375,18 @@ class Generator(nn.Module):
             N.check(lib.fd_source_conv_fwd(N.ptr(har), N.ptr(src["w_t"]), N.ptr(src["bias"]), N.ptr(xs_src), B, S, Co,
                                            src["k"], src["s"], src["p"], st), "fd_source_conv_fwd")
             # x = ups[i](lrelu(x)) + x_source  -> X (fp32 master) and PA = lrelu(X) planes
-            X = torch.empty((B, Lo, Co), **f32)
             PA = torch.empty((2, B, Lo, Co), **i16)
+            last_stage = i == self.num_upsamples - 1
+            if self._stage_fused(pk, i, Co):     # the residual stream lives in the planes only: no fp32 master
+                self._conv(up, cur, B, L, addend=xs_src, out_planes=PA, act=N.ACT_LRELU, act_slope=LRELU_SLOPE)
+                del xs_src
+                cur = self._stage_fused_run(pk, i, PA, B, Lo, Co, 0.01 if last_stage else LRELU_SLOPE)
+                L = Lo
+                del PA
+                continue
+            X = torch.empty((B, Lo, Co), **f32)
             self._conv(up, cur, B, L, addend=xs_src, out_f32=X, out_planes=PA, act=N.ACT_LRELU, act_slope=LRELU_SLOPE)
             del xs_src
-            last_stage = i == self.num_upsamples - 1
             XS = torch.empty((B, Lo, Co), **f32)
             nxt = torch.empty((2, B, Lo, Co), **i16)      # lrelu(xs / nk): next stage input (slope 0.01 at the end)
             PB = torch.empty((2, B, Lo, Co), **i16)
