@@ -56,10 +56,10 @@ class ResPairDesc(ctypes.Structure):
     """struct fd_respair_desc (include/fishdiff_b200.h)."""
     _fields_ = [
         ("in_planes", c_void_p), ("w1", c_void_p), ("w2", c_void_p), ("b1", c_void_p), ("b2", c_void_p),
-        ("out_planes", c_void_p), ("out_f32", c_void_p),
+        ("out_planes", c_void_p),
         ("B", c_int), ("T", c_int), ("C", c_int), ("k1", c_int), ("d1", c_int), ("k2", c_int),
         ("w1_inv_scale", c_float), ("w2_inv_scale", c_float), ("in_slope", c_float), ("out_slope", c_float),
-        ("planes_scale", c_float), ("out_accum", c_int), ("prec", c_int),
+        ("planes_scale", c_float), ("prec", c_int),
     ]
 
 
@@ -97,7 +97,7 @@ _SIGS = {
     "fd_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_longlong), c_int]),
     "fd_split_ncw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fd_split_nwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p]),
-    "fd_lrelu_split": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_float, c_int, c_void_p]),
+    "fd_mrf_finish": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_longlong, c_float, c_float, c_float, c_int, c_void_p]),
     "fd_transpose_nwc_to_ncw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fd_transpose_ncw_to_nwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fd_pack_weight": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_int, c_void_p]),
@@ -277,17 +277,24 @@ def respair_supported(C: int, k1: int, d1: int, k2: int) -> bool:
     return bool(lib().fd_respair_supported(C, k1, d1, k2))
 
 
-def respair(in_planes, w1, w2, b1, b2, B, T, C, k1, d1, k2, *, out_planes=None, out_f32=None, out_accum=False,
-            w1_inv_scale=1.0, w2_inv_scale=1.0, in_slope=0.1, out_slope=0.1, planes_scale=1.0, prec=PREC_F16):
-    """Fused ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) on planes of lrelu(x) (fd_respair_fwd)."""
+def respair(in_planes, w1, w2, b1, b2, B, T, C, k1, d1, k2, *, out_planes, w1_inv_scale=1.0, w2_inv_scale=1.0,
+            in_slope=0.1, out_slope=0.1, planes_scale=1.0, prec=PREC_F16):
+    """Fused ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) on planes of lrelu(x) -> planes of lrelu(x') (fd_respair_fwd)."""
     d = ResPairDesc()
     d.in_planes, d.w1, d.w2, d.b1, d.b2 = ptr(in_planes), ptr(w1), ptr(w2), ptr(b1), ptr(b2)
-    d.out_planes, d.out_f32 = ptr(out_planes), ptr(out_f32)
+    d.out_planes = ptr(out_planes)
     d.B, d.T, d.C, d.k1, d.d1, d.k2 = B, T, C, k1, d1, k2
     d.w1_inv_scale, d.w2_inv_scale = w1_inv_scale, w2_inv_scale
     d.in_slope, d.out_slope, d.planes_scale = in_slope, out_slope, planes_scale
-    d.out_accum, d.prec = int(out_accum), prec
+    d.prec = prec
     check(lib().fd_respair_fwd(ctypes.byref(d), stream_ptr(in_planes.device)), "fd_respair_fwd")
+
+
+def mrf_finish(ins, out, *, in_slope=0.1, scale=1.0, out_slope=0.1, prec=PREC_F16):
+    """out planes = split(lrelu(sum_i invlrelu(ins[i]) * scale, out_slope))  (fd_mrf_finish)."""
+    arr = (c_void_p * len(ins))(*[ptr(t) for t in ins])
+    check(lib().fd_mrf_finish(arr, len(ins), ptr(out), out.numel() // 2, in_slope, scale, out_slope, prec,
+                              stream_ptr(out.device)), "fd_mrf_finish")
 
 
 PROF_KINDS = {0: "linear/tc", 1: "linear/simt", 2: "gate/tc", 3: "gate/simt", 4: "res_skip/tc", 5: "res_skip/simt",

@@ -49,19 +49,27 @@ __global__ void k_split_nwc(const float* __restrict__ src, const uint8_t* __rest
   }
 }
 
-// planes = split(lrelu(src * scale, slope)): the multi-receptive-field average + LeakyReLU that feeds the next
-// upsampling stage (models.py:420,432)
-__global__ void k_lrelu_split(const float* __restrict__ src, uint16_t* __restrict__ planes, long long n, float scale,
-                              float slope, int prec) {
-  const long long n4 = n / 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+// out = split(lrelu((sum_i invlrelu(in_i)) * scale, out_slope)): the multi-receptive-field average + LeakyReLU that
+// feeds the next upsampling stage (models.py:420,426-434), on plane tensors
+struct MrfIn { const uint16_t* p[4]; };
+__global__ void k_mrf_finish(MrfIn in, int num, uint16_t* __restrict__ out, long long n, float in_slope_inv,
+                             float scale, float out_slope, int prec) {
+  const long long n8 = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long e = i * 4;
-    float v[4];
-    fd_load_f32<4>(src + e, v);
+    const size_t e = (size_t)i * 8;
+    float acc[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = fd_act(v[k] * scale, slope);
-    fd_store_planes<4>(planes, (size_t)n, (size_t)e, v, prec);
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int s = 0; s < num; ++s) {
+      float v[8];
+      fd_load_planes<8>(in.p[s], (size_t)n, e, v, prec);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k] >= 0.f ? v[k] : v[k] * in_slope_inv;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fd_act(acc[k] * scale, out_slope);
+    fd_store_planes<8>(out, (size_t)n, e, acc, prec);
   }
 }
 
@@ -397,10 +405,13 @@ int fd_split_nwc(const float* src, const uint8_t* mask, uint16_t* planes, int B,
   return 0;
 }
 
-int fd_lrelu_split(const float* src, uint16_t* planes, long long n, float scale, float slope, int prec, void* stream) {
+int fd_mrf_finish(const uint16_t* const* in, int num, uint16_t* out, long long n, float in_slope, float scale,
+                  float out_slope, int prec, void* stream) {
   FD_DEVICE_GUARD();
-  FD_REQUIRE(n % 4 == 0, "fd_lrelu_split: n=%lld must be a multiple of 4", n);
-  k_lrelu_split<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(src, planes, n, scale, slope, prec);
+  FD_REQUIRE(num >= 1 && num <= 4 && n % 8 == 0 && in_slope > 0.f, "fd_mrf_finish: num=%d n=%lld in_slope=%g", num, n, in_slope);
+  MrfIn m;
+  for (int i = 0; i < 4; ++i) m.p[i] = i < num ? in[i] : nullptr;
+  k_mrf_finish<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>(m, num, out, n, 1.f / in_slope, scale, out_slope, prec);
   FD_LAUNCHED();
   return 0;
 }

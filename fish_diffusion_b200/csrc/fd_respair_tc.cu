@@ -31,29 +31,35 @@
 
 namespace {
 
-constexpr int RP_MID_ROWS = 144;   // 128 rows of c1 output + 16 zero rows read by the trailing taps of c2
-constexpr int RP_RIN_MAX = 184;    // 128 + (k1-1)*d1 rounded up to 8, largest supported halo (k=11, d=5)
-
 struct FdResPairK {
   int B, T;
   int k1, d1, k2;
   int h1, h2;        // halos of c1 / c2 in rows
-  int r_in, r_out;   // rows of the input box (multiple of 8) / valid output rows per tile
+  int r_in, rb, nbox;   // rows of the input tile = nbox TMA boxes of rb rows (rb a multiple of 8)
+  int r_out;         // valid output rows per tile = MB*128 - (k2-1)
   int single;        // one product (hi planes only)
-  int mode;          // 0: planes out, 1: fp32 store, 2: fp32 reduce-add
   float inv_s1, inv_s2, s2;
   float in_slope_inv, out_slope, planes_scale;
   const float* b1;
   const float* b2;
 };
 
+// A tile is MB blocks of 128 rows with MB * C = 128: every tile holds the same number of elements whatever the
+// channel count, so the per-tile latency chain (TMA load -> GEMM1 -> epilogue -> GEMM2 -> epilogue -> TMA store) and
+// the (k-1)-row halo are amortised over 1024 rows at C = 16 instead of 128, and the epilogue of block j overlaps the
+// MMAs of block j+1.
 template <int C>
 struct RpCfg {
+  static constexpr int MB = 128 / C;
+  static constexpr int ROWS = MB * 128;
   static constexpr int BK_A = C >= 64 ? 64 : C;          // channels per shared-memory activation block
   static constexpr int NKB = C / BK_A;
   static constexpr int ROWB = BK_A * 2;                   // bytes per activation row
   static constexpr uint32_t SWZ_A = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;
   static constexpr uint32_t LT_A = ROWB == 128 ? 2u : ROWB == 64 ? 4u : 6u;
+  static constexpr int NBOX_MAX = (ROWS + 56 + 255) / 256;
+  static constexpr int RIN_MAX = ROWS + 56 + 8 * (NBOX_MAX - 1);
+  static constexpr int MID_ROWS = ROWS + 16;              // + zero rows read by the trailing taps of c2
   static constexpr int BKW = C == 128 ? 32 : BK_A;        // K extent of one weight unit
   static constexpr int WROWB = BKW * 2;
   static constexpr uint32_t LT_W = WROWB == 128 ? 2u : WROWB == 64 ? 4u : 6u;
@@ -62,29 +68,40 @@ struct RpCfg {
   static constexpr int GROUP_RAW = 16384 / UNIT_BYTES;
   static constexpr int GROUP = GROUP_RAW > 8 ? 8 : GROUP_RAW;   // weight units per pipeline stage
   static constexpr int STAGE_BYTES = GROUP * UNIT_BYTES;
-  static constexpr int IN_KB_BYTES = 2 * RP_RIN_MAX * ROWB;
+  static constexpr int IN_PLANE_BYTES = RIN_MAX * ROWB;
+  static constexpr int IN_KB_BYTES = 2 * IN_PLANE_BYTES;
   static constexpr int IN_BYTES = NKB * IN_KB_BYTES;
-  static constexpr int MID_PLANE_BYTES = RP_MID_ROWS * ROWB;
+  static constexpr int MID_PLANE_BYTES = MID_ROWS * ROWB;
   static constexpr int MID_KB_BYTES = 2 * MID_PLANE_BYTES;
-  static constexpr int MID_BYTES = NKB * MID_KB_BYTES;     // also the output staging (>= 128 * C * 4 bytes of fp32)
-  static constexpr int EPI_WARPS = C >= 32 ? 8 : 4;
-  static constexpr int HALVES = EPI_WARPS / 4;
+  static constexpr int MID_BYTES = NKB * MID_KB_BYTES;     // c1 output; afterwards the staging image of the output
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int GROUPS = C == 16 ? 2 : 1;            // warp groups taking alternate blocks
+  static constexpr int HALVES = C == 16 ? 1 : 2;            // warp groups splitting the columns of one block
   static constexpr int COLS = C / HALVES;                   // columns per epilogue thread
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int GTHREADS = EPI_THREADS / GROUPS;
   static constexpr int THREADS = 128 + EPI_THREADS;
-  static constexpr int TMEM_COLS = 4 * C < 32 ? 32 : 4 * C;  // acc1 [0,2C) | acc2 [2C,4C)
-  static constexpr int FB = C >= 32 ? 32 : C;               // fp32 staging: floats per box row
-  static constexpr int FROWB = FB * 4;
-  static constexpr uint32_t SWZ_F = FROWB == 128 ? 7u : 3u;
-  static constexpr int NFB = C / FB;
-  static constexpr int FBOX_BYTES = 128 * FROWB;
-  static constexpr int FIXED = 1024 + IN_BYTES + MID_BYTES + 2 * C * 4 + 256;
+  static constexpr int TMEM_COLS = 512;                     // acc1[j] at j*2C, acc2[j] at 256 + j*2C
+  static constexpr int NBAR = 2 + 3 * MB;
+  static constexpr int FIXED = 1024 + IN_BYTES + MID_BYTES + 2 * C * 4 + (NBAR + 16) * 8 + 64;
   static constexpr int RAW_STAGES = (227 * 1024 - FIXED) / STAGE_BYTES;
   static constexpr int NUM_STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
   static constexpr int SMEM_BYTES = FIXED + NUM_STAGES * STAGE_BYTES;
   static_assert(NUM_STAGES >= 2, "weight ring needs two stages");
-  static_assert(NFB * FBOX_BYTES <= MID_BYTES, "fp32 staging must fit the mid tile");
+  static_assert(IN_PLANE_BYTES % 1024 == 0 || (ROWB == 64 && IN_PLANE_BYTES % 512 == 0) || (ROWB == 32 && IN_PLANE_BYTES % 256 == 0),
+                "plane regions must start on a swizzle-pattern boundary");
 };
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
 
@@ -111,14 +128,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sm
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -127,8 +136,9 @@ template <int C, int PREC>
 __global__ void __launch_bounds__((RpCfg<C>::THREADS), 1)
 fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
-                     const FdResPairK p) {
+                     const __grid_constant__ CUtensorMap tm_out_last, const FdResPairK p) {
   using K = RpCfg<C>;
+  constexpr int MB = K::MB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* in_s = smem;
@@ -139,10 +149,10 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   uint64_t* w_empty = w_full + K::NUM_STAGES;
   uint64_t* in_full = w_empty + K::NUM_STAGES;
   uint64_t* in_empty = in_full + 1;
-  uint64_t* acc1_full = in_empty + 1;
-  uint64_t* mid_ready = acc1_full + 1;
-  uint64_t* acc2_full = mid_ready + 1;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc2_full + 1);
+  uint64_t* acc1_full = in_empty + 1;      // [MB]
+  uint64_t* mid_ready = acc1_full + MB;    // [MB]
+  uint64_t* acc2_full = mid_ready + MB;    // [MB]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc2_full + MB);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -150,12 +160,14 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   const int num_tiles = p.B * tiles_t;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_in); prefetch_tmap(&tm_w1); prefetch_tmap(&tm_w2); prefetch_tmap(&tm_out);
+    prefetch_tmap(&tm_in); prefetch_tmap(&tm_w1); prefetch_tmap(&tm_w2); prefetch_tmap(&tm_out); prefetch_tmap(&tm_out_last);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < K::NUM_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(in_full, 1); mbar_init(in_empty, K::EPI_WARPS);
-    mbar_init(acc1_full, 1); mbar_init(mid_ready, K::EPI_WARPS); mbar_init(acc2_full, 1);
+    for (int j = 0; j < MB; ++j) {
+      mbar_init(&acc1_full[j], 1); mbar_init(&mid_ready[j], K::EPI_WARPS / K::GROUPS); mbar_init(&acc2_full[j], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -166,36 +178,38 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   // biases; the 16 trailing rows of the mid tile are zero for the whole kernel
   for (int i = threadIdx.x; i < C; i += blockDim.x) { bias_s[i] = p.b1[i]; bias_s[C + i] = p.b2[i]; }
   for (int i = threadIdx.x; i < K::NKB * 2 * K::ROWB; i += blockDim.x)      // 16 rows = ROWB 16-byte chunks per plane
-    *reinterpret_cast<uint4*>(mid_s + (i / K::ROWB) * K::MID_PLANE_BYTES + 128 * K::ROWB + (i % K::ROWB) * 16) =
+    *reinterpret_cast<uint4*>(mid_s + (i / K::ROWB) * K::MID_PLANE_BYTES + K::ROWS * K::ROWB + (i % K::ROWB) * 16) =
         make_uint4(0, 0, 0, 0);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 2 * C;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
 
   const int units1 = p.k1 * K::UNITS_PER_TAP, units2 = p.k2 * K::UNITS_PER_TAP;
 
   if (warp == 0) {
-    // =========================================================== weight producer
+    // =========================================================== weight producer (the pair's weights, once per block)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int g2 = 0; g2 < 2; ++g2) {
           const CUtensorMap* tm = g2 == 0 ? &tm_w1 : &tm_w2;
           const int units = g2 == 0 ? units1 : units2;
-          for (int u0 = 0; u0 < units; u0 += K::GROUP) {
-            const int nb = min(K::GROUP, units - u0);
-            mbar_wait(&w_empty[stage], phase ^ 1);
-            mbar_expect_tx(&w_full[stage], nb * K::UNIT_BYTES);
-            uint8_t* slot = w_s + stage * K::STAGE_BYTES;
-            for (int g = 0; g < nb; ++g) {
-              const int u = u0 + g;
-              const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
-              tma_load_3d(slot + g * K::UNIT_BYTES, tm, &w_full[stage], tap * C + kw * K::BKW, 0, 0);
+          for (int j = 0; j < MB; ++j) {
+            for (int u0 = 0; u0 < units; u0 += K::GROUP) {
+              const int nb = min(K::GROUP, units - u0);
+              mbar_wait(&w_empty[stage], phase ^ 1);
+              mbar_expect_tx(&w_full[stage], nb * K::UNIT_BYTES);
+              uint8_t* slot = w_s + stage * K::STAGE_BYTES;
+              for (int g = 0; g < nb; ++g) {
+                const int u = u0 + g;
+                const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
+                tma_load_3d(slot + g * K::UNIT_BYTES, tm, &w_full[stage], tap * C + kw * K::BKW, 0, 0);
+              }
+              if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
             }
-            if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -209,129 +223,201 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         mbar_wait(in_empty, (it & 1) ^ 1);
         mbar_expect_tx(in_full, K::NKB * 2 * p.r_in * K::ROWB);
         for (int kb = 0; kb < K::NKB; ++kb)
-          tma_load_4d(in_s + kb * K::IN_KB_BYTES, &tm_in, in_full, kb * K::BK_A, t0 - p.h2 - p.h1, b, 0);
+          for (int pl = 0; pl < 2; ++pl)
+            for (int bx = 0; bx < p.nbox; ++bx)
+              tma_load_4d(in_s + kb * K::IN_KB_BYTES + pl * K::IN_PLANE_BYTES + bx * p.rb * K::ROWB, &tm_in, in_full,
+                          kb * K::BK_A, t0 - p.h2 - p.h1 + bx * p.rb, b, pl);
       }
     }
   } else if (warp == 1) {
     // =========================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t fmt = PREC == FD_F16 ? 0u : 1u;
-      const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc_2c = idesc_base | ((uint32_t)((2 * C) >> 3) << 17);
-      const uint32_t idesc_c = idesc_base | ((uint32_t)(C >> 3) << 17);
-      constexpr uint32_t SBO_A = 8 * K::ROWB, SBO_W = 8 * K::WROWB;
-      int stage = 0; uint32_t phase = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        for (int g2 = 0; g2 < 2; ++g2) {
-          const int units = g2 == 0 ? units1 : units2;
-          const uint32_t d_tmem = g2 == 0 ? acc1 : acc2;
-          const uint32_t a_base = g2 == 0 ? smem_u32(in_s) : smem_u32(mid_s);
-          const uint32_t a_kb = g2 == 0 ? K::IN_KB_BYTES : K::MID_KB_BYTES;
-          const uint32_t a_plane = g2 == 0 ? (uint32_t)p.r_in * K::ROWB : (uint32_t)K::MID_PLANE_BYTES;
-          const int dil = g2 == 0 ? p.d1 : 1;
-          if (g2 == 0) mbar_wait(in_full, it & 1); else mbar_wait(mid_ready, it & 1);
-          tc_fence_after();
+    // The WHOLE warp runs the loops (every value is warp-uniform, so descriptors and addresses stay in uniform
+    // registers); only the tcgen05 instructions are issued by one elected lane.  With the loops inside `if (lane == 0)`
+    // the compiler wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / branch sequence (~100 cycles per instruction),
+    // which is what bounds the narrow-N shapes (an N = 16..64 instruction occupies the tensor core for 8..32 cycles).
+    const uint32_t fmt = PREC == FD_F16 ? 0u : 1u;
+    const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_2c = idesc_base | ((uint32_t)((2 * C) >> 3) << 17);
+    const uint32_t idesc_c = idesc_base | ((uint32_t)(C >> 3) << 17);
+    constexpr uint32_t SBO_A = 8 * K::ROWB, SBO_W = 8 * K::WROWB;
+    constexpr uint64_t DESC_HI_A = ((uint64_t)((SBO_A >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)K::LT_A << 61) | ((uint64_t)1 << 16);
+    constexpr uint64_t DESC_HI_W = ((uint64_t)((SBO_W >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)K::LT_W << 61) | ((uint64_t)1 << 16);
+    const bool single = p.single != 0;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+      for (int g2 = 0; g2 < 2; ++g2) {
+        const int units = g2 == 0 ? units1 : units2;
+        const uint32_t a_base = g2 == 0 ? smem_u32(in_s) : smem_u32(mid_s);
+        const uint32_t a_kb = g2 == 0 ? K::IN_KB_BYTES : K::MID_KB_BYTES;
+        const uint32_t a_plane = g2 == 0 ? (uint32_t)K::IN_PLANE_BYTES : (uint32_t)K::MID_PLANE_BYTES;
+        const uint32_t tap_bytes = (uint32_t)(g2 == 0 ? p.d1 : 1) * K::ROWB;
+        if (g2 == 0) { mbar_wait(in_full, it & 1); tc_fence_after(); }
+#pragma unroll 1
+        for (int j = 0; j < MB; ++j) {
+          const uint32_t d_tmem = (g2 == 0 ? acc1 : acc2) + j * 2 * C;
+          if (g2 == 1) {   // GEMM2 of block j reads mid rows of blocks j and j+1 (and the residual-initialised accumulator)
+            mbar_wait(&mid_ready[j + 1 < MB ? j + 1 : j], it & 1);
+            tc_fence_after();
+          }
+          int u = 0;
+#pragma unroll 1
           for (int u0 = 0; u0 < units; u0 += K::GROUP) {
             const int nb = min(K::GROUP, units - u0);
             mbar_wait(&w_full[stage], phase);
             tc_fence_after();
-            for (int g = 0; g < nb; ++g) {
-              const int u = u0 + g;
+            const uint32_t w_stage = smem_u32(w_s + stage * K::STAGE_BYTES);
+#pragma unroll 1
+            for (int g = 0; g < nb; ++g, ++u) {
               const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
               const int ch = kw * K::BKW;
-              const uint32_t a_hi = a_base + (ch / K::BK_A) * a_kb + (uint32_t)(tap * dil) * K::ROWB + (ch % K::BK_A) * 2;
-              const uint32_t w_addr = smem_u32(w_s + stage * K::STAGE_BYTES + g * K::UNIT_BYTES);
+              const uint32_t a_hi = a_base + (ch / K::BK_A) * a_kb + (uint32_t)(j * 128) * K::ROWB + (uint32_t)tap * tap_bytes +
+                                    (ch % K::BK_A) * 2;
+              const uint64_t da_hi = DESC_HI_A | (uint64_t)((a_hi & 0x3FFFF) >> 4);
+              const uint64_t da_lo = DESC_HI_A | (uint64_t)(((a_hi + a_plane) & 0x3FFFF) >> 4);
+              const uint64_t dw = DESC_HI_W | (uint64_t)(((w_stage + g * K::UNIT_BYTES) & 0x3FFFF) >> 4);
+              const uint32_t first = (g2 == 1 || u != 0) ? 1u : 0u;
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < K::BKW / 16; ++k) {
-                const uint64_t da_hi = make_kmajor_desc(a_hi + k * 32, SBO_A, K::LT_A);
-                const uint64_t dw = make_kmajor_desc(w_addr + k * 32, SBO_W, K::LT_W);
-                const uint32_t accum = (g2 == 1 || u != 0 || k != 0) ? 1u : 0u;
-                if (!p.single) {
-                  const uint64_t da_lo = make_kmajor_desc(a_hi + a_plane + k * 32, SBO_A, K::LT_A);
-                  umma_f16(d_tmem, da_hi, dw, idesc_2c, accum);     // a_hi x [w_hi | w_lo] -> columns [0,2C)
-                  umma_f16(d_tmem, da_lo, dw, idesc_c, 1u);         // a_lo x w_hi         -> columns [0,C)
-                } else {
-                  umma_f16(d_tmem, da_hi, dw, idesc_c, accum);
+                for (int k = 0; k < K::BKW / 16; ++k) {
+                  const uint32_t accum = (k != 0) ? 1u : first;
+                  if (!single) {
+                    umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_2c, accum);     // a_hi x [w_hi | w_lo] -> [0,2C)
+                    umma_f16(d_tmem, da_lo + 2 * k, dw + 2 * k, idesc_c, 1u);         // a_lo x w_hi         -> [0,C)
+                  } else {
+                    umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_c, accum);
+                  }
                 }
               }
+              __syncwarp();
             }
-            umma_commit(&w_empty[stage]);
+            if (elect_one()) umma_commit(&w_empty[stage]);
+            __syncwarp();
             if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(g2 == 0 ? acc1_full : acc2_full);
+          if (elect_one()) umma_commit(g2 == 0 ? &acc1_full[j] : &acc2_full[j]);
+          __syncwarp();
         }
       }
     }
   } else if (warp >= 4) {
     // =========================================================== epilogue
     const int q = warp % 4;
-    const int half = (warp - 4) / 4;
+    const int wg = (warp - 4) / 4;
+    const int grp = K::GROUPS == 2 ? wg : 0;          // which blocks this warp takes (j % GROUPS == grp)
+    const int half = K::HALVES == 2 ? wg : 0;         // which columns of a block
     const int row = q * 32 + lane;
     const int col_base = half * K::COLS;
     const int etid = threadIdx.x - 128;
+    const bool issuer = (etid % K::GTHREADS) == 0;    // first thread of a group issues that group's TMA stores
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t in_u = smem_u32(in_s), mid_u = smem_u32(mid_s);
     const float slope_mid = 0.1f;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / tiles_t, t0 = (tile % tiles_t) * p.r_out;
-      // ---- phase 1: GEMM1 done
-      mbar_wait(acc1_full, it & 1);
-      tc_fence_after();
-      mbar_wait(in_full, it & 1);                    // visibility of the TMA-written input tile to these threads
-      // the staging tile (= mid tile) of the previous output must have been read by its TMA stores
-      if (etid == 0) bulk_wait_read0();
-      asm volatile("bar.sync 1, %0;" ::"r"(K::EPI_THREADS) : "memory");
-      if (p.mode != 0) {   // the fp32 staging image overlaps the zero rows of the mid tile: restore them
-        for (int i = etid; i < K::NKB * 2 * K::ROWB; i += K::EPI_THREADS)
-          *reinterpret_cast<uint4*>(mid_s + (i / K::ROWB) * K::MID_PLANE_BYTES + 128 * K::ROWB + (i % K::ROWB) * 16) =
-              make_uint4(0, 0, 0, 0);
-      }
-      // (a) residual + c2 bias -> accumulator 2 (pre-scaled by the weight prescale of c2), zeros in the [w_lo] half
-      {
-        const int n = row + p.h1 + p.h2;
-        const uint32_t lo_off = (uint32_t)p.r_in * K::ROWB;
+      // ---- phase 1 per block: GEMM1 done -> residual into accumulator 2, c1 output into the mid tile
+#pragma unroll 1
+      for (int j = grp; j < MB; j += K::GROUPS) {
+        mbar_wait(&acc1_full[j], it & 1);
+        tc_fence_after();
+        if (j == grp) {
+          mbar_wait(in_full, it & 1);                  // visibility of the TMA-written input tile to these threads
+          // the staging image (= mid tile) of the previous tile must have been read by its TMA stores
+          if (issuer) bulk_wait_read0();
+          asm volatile("bar.sync 3, %0;" ::"r"(K::EPI_THREADS) : "memory");
+        }
+        const int m = j * 128 + row;                   // row of the mid tile
+        // (a) residual + c2 bias -> accumulator 2 (pre-scaled by the weight prescale of c2), zeros in the [w_lo] half
+        {
+          const int n = m + p.h1 + p.h2;
 #pragma unroll
-        for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
-          const int col = col_base + c16 * 16;
-          const int kb = col / K::BK_A, cc = col % K::BK_A;
-          const uint32_t base = in_u + kb * K::IN_KB_BYTES;
-          float v[16];
+          for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+            const int col = col_base + c16 * 16;
+            const int kb = col / K::BK_A, cc = col % K::BK_A;
+            const uint32_t base = in_u + kb * K::IN_KB_BYTES;
+            float v[16];
 #pragma unroll
-          for (int hq = 0; hq < 2; ++hq) {
-            const uint32_t off = swz((uint32_t)n * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
-            const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + lo_off + off);
-            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            for (int hq = 0; hq < 2; ++hq) {
+              const uint32_t off = swz((uint32_t)n * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+              const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + K::IN_PLANE_BYTES + off);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a0, a1;
-              fd_combine2(hw[j], lw[j], PREC, a0, a1);
-              a0 = a0 >= 0.f ? a0 : a0 * p.in_slope_inv;
-              a1 = a1 >= 0.f ? a1 : a1 * p.in_slope_inv;
-              v[hq * 8 + 2 * j] = (a0 + bias_s[C + col + hq * 8 + 2 * j]) * p.s2;
-              v[hq * 8 + 2 * j + 1] = (a1 + bias_s[C + col + hq * 8 + 2 * j + 1]) * p.s2;
+              for (int jj = 0; jj < 4; ++jj) {
+                float a0, a1;
+                fd_combine2(hw[jj], lw[jj], PREC, a0, a1);
+                a0 = a0 >= 0.f ? a0 : a0 * p.in_slope_inv;
+                a1 = a1 >= 0.f ? a1 : a1 * p.in_slope_inv;
+                v[hq * 8 + 2 * jj] = (a0 + bias_s[C + col + hq * 8 + 2 * jj]) * p.s2;
+                v[hq * 8 + 2 * jj + 1] = (a1 + bias_s[C + col + hq * 8 + 2 * jj + 1]) * p.s2;
+              }
+            }
+            tmem_st16(acc2 + j * 2 * C + lane_addr + col, v);
+            if (!p.single) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0.f;
+              tmem_st16(acc2 + j * 2 * C + lane_addr + C + col, v);
             }
           }
-          tmem_st16(acc2 + lane_addr + col, v);
-          if (!p.single) {
+          tmem_st_wait();
+        }
+        // (b) accumulator 1 -> bias, LeakyReLU, zero outside [0,T), split planes -> mid tile (c2's A operand)
+        {
+          const int t = t0 - p.h2 + m;
+          const bool ok = t >= 0 && t < p.T;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-            tmem_st16(acc2 + lane_addr + C + col, v);
+          for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+            const int col = col_base + c16 * 16;
+            float a[16], a2[16];
+            tmem_ld16_nowait(acc1 + j * 2 * C + lane_addr + col, a);
+            if (!p.single) tmem_ld16_nowait(acc1 + j * 2 * C + lane_addr + C + col, a2);
+            tmem_wait16(a);
+            if (!p.single) {
+              tmem_wait16(a2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) a[i] += a2[i];
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              float y0 = a[2 * jj] * p.inv_s1 + bias_s[col + 2 * jj];
+              float y1 = a[2 * jj + 1] * p.inv_s1 + bias_s[col + 2 * jj + 1];
+              y0 = ok ? fd_act(y0, slope_mid) : 0.f;
+              y1 = ok ? fd_act(y1, slope_mid) : 0.f;
+              fd_split2(y0, y1, PREC, hi[jj], lo[jj]);
+            }
+            const int kb = col / K::BK_A, cc = col % K::BK_A;
+            const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              const uint32_t off = swz((uint32_t)m * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+              sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
+              sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
+            }
           }
         }
-        tmem_st_wait();
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&mid_ready[j]);
+          if (j + K::GROUPS >= MB) mbar_arrive(in_empty);      // this warp's last read of the input tile
+        }
       }
-      // (b) accumulator 1 -> bias, LeakyReLU, zero outside [0,T), split planes -> mid tile (c2's A operand)
-      {
-        const int t = t0 - p.h2 + row;
-        const bool ok = t >= 0 && t < p.T;
+
+      // ---- phase 2 per block: GEMM2 done (accumulator 2 = (x + b2) * s2 + conv products) -> output planes via TMA
+#pragma unroll 1
+      for (int j = grp; j < MB; j += K::GROUPS) {
+        mbar_wait(&acc2_full[j], it & 1);
+        tc_fence_after();
+        const int m = j * 128 + row;
 #pragma unroll
         for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
           const int col = col_base + c16 * 16;
           float a[16], a2[16];
-          tmem_ld16_nowait(acc1 + lane_addr + col, a);
-          if (!p.single) tmem_ld16_nowait(acc1 + lane_addr + C + col, a2);
+          tmem_ld16_nowait(acc2 + j * 2 * C + lane_addr + col, a);
+          if (!p.single) tmem_ld16_nowait(acc2 + j * 2 * C + lane_addr + C + col, a2);
           tmem_wait16(a);
           if (!p.single) {
             tmem_wait16(a2);
@@ -340,86 +426,32 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           }
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float y0 = a[2 * j] * p.inv_s1 + bias_s[col + 2 * j];
-            float y1 = a[2 * j + 1] * p.inv_s1 + bias_s[col + 2 * j + 1];
-            y0 = ok ? fd_act(y0, slope_mid) : 0.f;
-            y1 = ok ? fd_act(y1, slope_mid) : 0.f;
-            fd_split2(y0, y1, PREC, hi[j], lo[j]);
-          }
+          for (int jj = 0; jj < 8; ++jj)
+            fd_split2(fd_act(a[2 * jj] * p.inv_s2, p.out_slope) * p.planes_scale,
+                      fd_act(a[2 * jj + 1] * p.inv_s2, p.out_slope) * p.planes_scale, PREC, hi[jj], lo[jj]);
           const int kb = col / K::BK_A, cc = col % K::BK_A;
           const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
 #pragma unroll
           for (int hq = 0; hq < 2; ++hq) {
-            const uint32_t off = swz((uint32_t)row * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+            const uint32_t off = swz((uint32_t)m * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
             sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
             sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
           }
         }
-      }
-      fence_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(mid_ready); mbar_arrive(in_empty); }
-
-      // ---- phase 2: GEMM2 done (accumulator 2 = (x + b2) * s2 + conv products)
-      mbar_wait(acc2_full, it & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
-        const int col = col_base + c16 * 16;
-        float a[16], a2[16];
-        tmem_ld16_nowait(acc2 + lane_addr + col, a);
-        if (!p.single) tmem_ld16_nowait(acc2 + lane_addr + C + col, a2);
-        tmem_wait16(a);
-        if (!p.single) {
-          tmem_wait16(a2);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] += a2[i];
-        }
-        if (p.mode == 0) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            fd_split2(fd_act(a[2 * j] * p.inv_s2, p.out_slope) * p.planes_scale,
-                      fd_act(a[2 * j + 1] * p.inv_s2, p.out_slope) * p.planes_scale, PREC, hi[j], lo[j]);
-          const int kb = col / K::BK_A, cc = col % K::BK_A;
-          const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
-#pragma unroll
-          for (int hq = 0; hq < 2; ++hq) {
-            const uint32_t off = swz((uint32_t)row * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
-            sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
-            sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
-          }
-        } else {
-          const int fbx = col / K::FB, cc = col % K::FB;
-          const uint32_t base = mid_u + fbx * K::FBOX_BYTES;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t off = swz((uint32_t)row * K::FROWB + (uint32_t)(cc / 4 + j) * 16, K::SWZ_F);
-            sts_u4(base + off, __float_as_uint(a[4 * j] * p.inv_s2), __float_as_uint(a[4 * j + 1] * p.inv_s2),
-                   __float_as_uint(a[4 * j + 2] * p.inv_s2), __float_as_uint(a[4 * j + 3] * p.inv_s2));
-          }
-        }
-      }
-      fence_async_smem();
-      tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"r"(K::EPI_THREADS) : "memory");
-      if (etid == 0) {
-        if (p.mode == 0) {
+        fence_async_smem();
+        tc_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(K::GTHREADS) : "memory");
+        if (issuer) {
+          const CUtensorMap* tm = j == MB - 1 ? &tm_out_last : &tm_out;
           for (int kb = 0; kb < K::NKB; ++kb)
             for (int pl = 0; pl < 2; ++pl)
-              tma_store_4d(&tm_out, mid_u + kb * K::MID_KB_BYTES + pl * K::MID_PLANE_BYTES, kb * K::BK_A, t0, b, pl);
-        } else {
-          for (int fbx = 0; fbx < K::NFB; ++fbx) {
-            if (p.mode == 1) tma_store_3d(&tm_out, mid_u + fbx * K::FBOX_BYTES, fbx * K::FB, t0, b);
-            else tma_reduce_add_3d(&tm_out, mid_u + fbx * K::FBOX_BYTES, fbx * K::FB, t0, b);
-          }
+              tma_store_4d(tm, mid_u + kb * K::MID_KB_BYTES + pl * K::MID_PLANE_BYTES + (uint32_t)(j * 128) * K::ROWB,
+                           kb * K::BK_A, t0 + j * 128, b, pl);
+          bulk_commit();
         }
-        bulk_commit();
       }
     }
-    if (etid == 0) bulk_wait0();
+    if (issuer) bulk_wait0();
   }
 
   // ---------------------------------------------------------------- teardown
@@ -454,20 +486,6 @@ int make_planes_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, in
   return 0;
 }
 
-int make_f32_map(CUtensorMap* m, const float* ptr, int B, int T, int C, int fb, int rows) {
-  PFN_tmapEncodeTiled enc = get_encode();
-  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
-  cuuint32_t box[3] = {(cuuint32_t)fb, (cuuint32_t)rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(fb * 4), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed: %d (B=%d T=%d C=%d)", (int)r, B, T, C);
-  return 0;
-}
-
 // packed weights [2][C][K] (uint16): box {bkw, C, 2}
 int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw) {
   PFN_tmapEncodeTiled enc = get_encode();
@@ -484,17 +502,25 @@ int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw
 }
 
 template <int C, int PREC>
-int launch_respair(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t stream) {
+int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) {
   using K = RpCfg<C>;
-  CUtensorMap tin, tw1, tw2, tout;
-  int rc = make_planes_map(&tin, d.in_planes, p.B, p.T, C, K::BK_A, p.r_in, 2);
+  // tile geometry: MB blocks of 128 rows; the input tile is nbox TMA boxes of rb rows
+  const int need = K::ROWS + (p.k1 - 1) * p.d1;
+  p.nbox = (need + 255) / 256;
+  p.rb = ((need + p.nbox - 1) / p.nbox + 7) / 8 * 8;
+  p.r_in = p.nbox * p.rb;
+  p.r_out = K::ROWS - (p.k2 - 1);
+  FD_REQUIRE(p.r_in <= K::RIN_MAX && p.rb <= 256, "fd_respair_fwd: input tile of %d rows exceeds the shared-memory tile", p.r_in);
+  CUtensorMap tin, tw1, tw2, tout, tout_last;
+  int rc = make_planes_map(&tin, d.in_planes, p.B, p.T, C, K::BK_A, p.rb, 1);
   if (rc) return rc;
   rc = make_wpair_map(&tw1, d.w1, C, p.k1 * C, K::BKW);
   if (rc) return rc;
   rc = make_wpair_map(&tw2, d.w2, C, p.k2 * C, K::BKW);
   if (rc) return rc;
-  if (p.mode == 0) rc = make_planes_map(&tout, d.out_planes, p.B, p.T, C, K::BK_A, p.r_out, 1);
-  else rc = make_f32_map(&tout, d.out_f32, p.B, p.T, C, K::FB, p.r_out);
+  rc = make_planes_map(&tout, d.out_planes, p.B, p.T, C, K::BK_A, 128, 1);
+  if (rc) return rc;
+  rc = make_planes_map(&tout_last, d.out_planes, p.B, p.T, C, K::BK_A, 128 - (p.k2 - 1), 1);
   if (rc) return rc;
   auto kern = fd_respair_tc_kernel<C, PREC>;
   static bool attr_set[FD_MAX_DEVICES] = {false};
@@ -505,7 +531,7 @@ int launch_respair(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t s
   }
   const int tiles = p.B * ((p.T + p.r_out - 1) / p.r_out);
   const int sms = fd_device_sms(dev);
-  kern<<<tiles < sms ? tiles : sms, K::THREADS, K::SMEM_BYTES, stream>>>(tin, tw1, tw2, tout, p);
+  kern<<<tiles < sms ? tiles : sms, K::THREADS, K::SMEM_BYTES, stream>>>(tin, tw1, tw2, tout, tout_last, p);
   FD_CHECK_CUDA(cudaGetLastError());
   fd_count_launch(1);
   return 0;
@@ -521,8 +547,8 @@ int launch_respair_prec(const fd_respair_desc& d, const FdResPairK& p, cudaStrea
 extern "C" int fd_respair_supported(int C, int k1, int d1, int k2) {
   if (C != 16 && C != 32 && C != 64 && C != 128) return 0;
   if (k1 < 1 || k2 < 1 || (k1 & 1) == 0 || (k2 & 1) == 0 || d1 < 1) return 0;
-  if (k2 - 1 > RP_MID_ROWS - 128) return 0;
-  if (128 + (k1 - 1) * d1 > RP_RIN_MAX) return 0;
+  if (k2 - 1 > 16) return 0;                             // zero rows behind the mid tile
+  if ((k1 - 1) * d1 > 56) return 0;                      // halo rows of the input tile
   if ((k2 - 1) / 2 > (k1 - 1) / 2 * d1) return 0;       // the residual rows must lie inside the input tile
   return 1;
 }
@@ -533,18 +559,14 @@ extern "C" int fd_respair_fwd(const fd_respair_desc* d, void* stream) {
   FD_REQUIRE(fd_respair_supported(d->C, d->k1, d->d1, d->k2), "fd_respair_fwd: unsupported shape C=%d k1=%d d1=%d k2=%d",
              d->C, d->k1, d->d1, d->k2);
   FD_REQUIRE(d->B > 0 && d->T > 0, "fd_respair_fwd: bad shape B=%d T=%d", d->B, d->T);
-  FD_REQUIRE(d->in_planes && d->w1 && d->w2 && d->b1 && d->b2, "fd_respair_fwd: null pointer");
-  FD_REQUIRE((d->out_planes != nullptr) != (d->out_f32 != nullptr), "fd_respair_fwd: exactly one of out_planes / out_f32");
+  FD_REQUIRE(d->in_planes && d->w1 && d->w2 && d->b1 && d->b2 && d->out_planes, "fd_respair_fwd: null pointer");
   FD_REQUIRE(d->in_slope > 0.f, "fd_respair_fwd: the input LeakyReLU slope must be positive (it is inverted)");
   FD_REQUIRE((const void*)d->out_planes != (const void*)d->in_planes, "fd_respair_fwd: in-place is not supported (halo reads)");
   FdResPairK p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.T = d->T; p.k1 = d->k1; p.d1 = d->d1; p.k2 = d->k2;
   p.h1 = (d->k1 - 1) / 2 * d->d1; p.h2 = (d->k2 - 1) / 2;
-  p.r_in = (128 + (d->k1 - 1) * d->d1 + 7) / 8 * 8;
-  p.r_out = 128 - (d->k2 - 1);
   p.single = (d->prec & FD_SINGLE) ? 1 : 0;
-  p.mode = d->out_planes != nullptr ? 0 : (d->out_accum ? 2 : 1);
   p.inv_s1 = d->w1_inv_scale; p.inv_s2 = d->w2_inv_scale; p.s2 = 1.f / d->w2_inv_scale;
   p.in_slope_inv = 1.f / d->in_slope; p.out_slope = d->out_slope; p.planes_scale = d->planes_scale;
   p.b1 = d->b1; p.b2 = d->b2;

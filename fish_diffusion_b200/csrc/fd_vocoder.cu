@@ -147,27 +147,45 @@ __global__ void k_sinegen_out(const float* __restrict__ f0, const float* __restr
     if (s0 + i < S) har[(size_t)b * S + s0 + i] = tanhf(lin[i]);
 }
 
-// 1 -> C strided conv of the excitation; w_t [k][C] (tap-major so lanes read consecutive channels)
-constexpr int SC_QT = 32;
+// 1 -> C strided conv of the excitation; w_t [k][C] (tap-major so lanes read consecutive channels).
+// HBM-bound (4 B/element written): a thread owns 4 consecutive channels x SC_R consecutive output rows, so a weight
+// float4 (L1-resident, coalesced over the channel groups) feeds 4*SC_R FMAs and every store is a float4; the slice of
+// the excitation a block needs sits in shared memory.
+constexpr int SC_R = 4;
 __global__ void k_source_conv(const float* __restrict__ har, const float* __restrict__ w_t,
                               const float* __restrict__ bias, float* __restrict__ out, long long S, long long S_out,
-                              int C, int k, int s, int p) {
+                              int C, int k, int s, int p, int rows_per_block) {
   extern __shared__ float win[];
   const int b = blockIdx.y;
-  const long long q0 = (long long)blockIdx.x * SC_QT;
-  const int wlen = (SC_QT - 1) * s + k;
-  const long long base = q0 * s - p;
-  for (int i = threadIdx.x; i < wlen; i += blockDim.x) {
-    const long long idx = base + i;
-    win[i] = (idx >= 0 && idx < S) ? har[(size_t)b * S + idx] : 0.f;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < SC_QT * C; idx += blockDim.x) {
-    const int q = idx / C, c = idx % C;
-    if (q0 + q >= S_out) continue;
-    float acc = bias[c];
-    for (int j = 0; j < k; ++j) acc = fmaf(win[q * s + j], w_t[(size_t)j * C + c], acc);
-    out[((size_t)b * S_out + q0 + q) * C + c] = acc;
+  const int cgroups = C / 4;
+  const int cg = threadIdx.x % cgroups, rg = threadIdx.x / cgroups;
+  const int wlen = (rows_per_block - 1) * s + k;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * cg);
+  for (long long q0 = (long long)blockIdx.x * rows_per_block; q0 < S_out; q0 += (long long)gridDim.x * rows_per_block) {
+    const long long base = q0 * s - p;
+    __syncthreads();
+    for (int i = threadIdx.x; i < wlen; i += blockDim.x) {
+      const long long idx = base + i;
+      win[i] = (idx >= 0 && idx < S) ? har[(size_t)b * S + idx] : 0.f;
+    }
+    __syncthreads();
+    const int r0 = rg * SC_R;
+    float4 acc[SC_R];
+#pragma unroll
+    for (int r = 0; r < SC_R; ++r) acc[r] = b4;
+    for (int j = 0; j < k; ++j) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_t + (size_t)j * C + 4 * cg));
+#pragma unroll
+      for (int r = 0; r < SC_R; ++r) {
+        const float h = win[(r0 + r) * s + j];
+        acc[r].x = fmaf(h, w4.x, acc[r].x); acc[r].y = fmaf(h, w4.y, acc[r].y);
+        acc[r].z = fmaf(h, w4.z, acc[r].z); acc[r].w = fmaf(h, w4.w, acc[r].w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SC_R; ++r)
+      if (q0 + r0 + r < S_out)
+        *reinterpret_cast<float4*>(out + ((size_t)b * S_out + q0 + r0 + r) * C + 4 * cg) = acc[r];
   }
 }
 
@@ -254,9 +272,15 @@ int fd_source_conv_fwd(const float* har, const float* w, const float* bias, floa
   FD_DEVICE_GUARD();
   const long long S_out = (S + 2LL * p - k) / s + 1;
   FD_REQUIRE(S_out > 0, "fd_source_conv_fwd: empty output");
-  const int wlen = (SC_QT - 1) * s + k;
-  dim3 grid((unsigned)((S_out + SC_QT - 1) / SC_QT), B);
-  k_source_conv<<<grid, 256, wlen * sizeof(float), (cudaStream_t)stream>>>(har, w, bias, out, S, S_out, C, k, s, p);
+  FD_REQUIRE(C % 4 == 0 && C <= 1024 && 1024 % C == 0, "fd_source_conv_fwd: C=%d must divide 1024", C);
+  const int rows_per_block = (256 / (C / 4)) * SC_R;
+  const int wlen = (rows_per_block - 1) * s + k;
+  long long gx = (S_out + rows_per_block - 1) / rows_per_block;
+  const long long cap = (148LL * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, B);
+  k_source_conv<<<grid, 256, wlen * sizeof(float), (cudaStream_t)stream>>>(har, w, bias, out, S, S_out, C, k, s, p,
+                                                                           rows_per_block);
   FD_LAUNCHED();
   return 0;
 }

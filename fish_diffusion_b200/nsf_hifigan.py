@@ -216,6 +216,26 @@ class Generator(nn.Module):
                                   bias=bias.repeat(F).contiguous(), backend=N.BACKEND_TC)
         return pc
 
+    def _pack_conv_folded_pair(self, conv, prec, device, F=2):
+        """Pack for the fused pair kernel on the time-folded view [T/F, F*C] (C = 16 -> 32): the conv becomes a
+        dilation-1 conv with K' = 2*max|row shift|+1 taps of (F*C x F*C) blocks (zero blocks where a shift does not
+        occur).  32-byte rows are what bounds the C = 16 stage (TMA row rate); 64-byte rows and a quarter of the tiles
+        cost 3x the tensor-core work, which is idle there."""
+        w = _effective_weight(conv).detach().to(device=device, dtype=torch.float32)
+        Co, Ci, K = w.shape
+        d = conv.dilation[0]
+        wf, srows = fold_conv_weight(w, d, F)                       # [F*Co, S*F*Ci], sorted row shifts
+        hmax = max(abs(srows[0]), abs(srows[-1]))
+        Kp = 2 * hmax + 1
+        W = torch.zeros((F * Co, Kp, F * Ci), dtype=torch.float32, device=device)
+        wf3 = wf.reshape(F * Co, len(srows), F * Ci)
+        for j, sr in enumerate(srows):
+            W[:, sr + hmax, :] = wf3[:, j, :]
+        w2 = W.reshape(F * Co, Kp * F * Ci).contiguous()
+        s = N.pow2_scale(w2)
+        bias = conv.bias.detach().to(device=device, dtype=torch.float32).repeat(F).contiguous()
+        return dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, K=Kp, d=1, bias=bias, F=F, C=F * Co)
+
     def _pack_convt(self, conv, prec, device):
         """ConvTranspose1d(Ci->Co, k, stride u, padding p) as a polyphase tap-GEMM: output row q of width u*Co
         holds output samples q*u + r;  W'[(r,co)][(delta,ci)] = w[ci,co, r + p - delta*u] when that tap exists."""
@@ -252,8 +272,12 @@ class Generator(nn.Module):
                                   s=nc.stride[0], p=nc.padding[0], C=nc.out_channels))
         for rb in self.resblocks:
             if isinstance(rb, ResBlock1):
-                pk["res"].append(dict(kind=1, c1=[self._pack_conv(c, prec, device) for c in rb.convs1],
-                                      c2=[self._pack_conv(c, prec, device) for c in rb.convs2]))
+                ent = dict(kind=1, c1=[self._pack_conv(c, prec, device) for c in rb.convs1],
+                           c2=[self._pack_conv(c, prec, device) for c in rb.convs2])
+                if rb.convs1[0].in_channels == 16 and self.fused and self.backend != "simt":
+                    ent["c1f"] = [self._pack_conv_folded_pair(c, prec, device) for c in rb.convs1]
+                    ent["c2f"] = [self._pack_conv_folded_pair(c, prec, device) for c in rb.convs2]
+                pk["res"].append(ent)
             else:
                 pk["res"].append(dict(kind=2, c=[self._pack_conv(c, prec, device) for c in rb.convs]))
         post = _effective_weight(self.conv_post).detach().to(device=device, dtype=torch.float32)   # [1, C, 7]
@@ -288,32 +312,32 @@ class Generator(nn.Module):
         return True
 
     def _stage_fused_run(self, pk, i, PA, B, Lo, Co, out_slope):
-        """MRF stage (models.py:426-432) on fused pairs.  PA = planes of lrelu(x, 0.1).  Each ResBlock chain runs
-        pair by pair on plane buffers (4 B/element in, 4 B/element out); the last pair of a chain adds its fp32 result
-        into XS by TMA reduce-add; one elementwise pass makes the next stage's input lrelu(XS / num_kernels)."""
-        dev = PA.device
+        """MRF stage (models.py:426-432) on fused pairs.  PA = planes of lrelu(x, 0.1).  Each ResBlock chain runs pair
+        by pair on plane buffers (4 B/element in, 4 B/element out); one elementwise pass over the three chain outputs
+        makes the next stage's input lrelu(sum / num_kernels)."""
         nk = self.num_kernels
         mma = pk["mma"]
-        XS = torch.empty((B, Lo, Co), dtype=torch.float32, device=dev)
-        bufs = [torch.empty_like(PA), torch.empty_like(PA)]
+        tmp = [torch.empty_like(PA), torch.empty_like(PA)]
+        outs = []
+        folded = all("c1f" in pk["res"][i * nk + j] for j in range(nk)) and Lo % 2 == 0 and all(
+            N.respair_supported(2 * Co, a["K"], 1, b["K"]) for j in range(nk)
+            for a, b in zip(pk["res"][i * nk + j].get("c1f", []), pk["res"][i * nk + j].get("c2f", [])))
+        if folded:                       # same memory viewed as [Lo/2, 2*Co] (see _pack_conv_folded_pair)
+            Lo, Co = Lo // 2, 2 * Co
         for j in range(nk):
             rb = pk["res"][i * nk + j]
             n = len(rb["c1"])
             src = PA
             for m in range(n):
-                c1, c2 = rb["c1"][m], rb["c2"][m]
-                kw = dict(w1_inv_scale=c1["inv"], w2_inv_scale=c2["inv"], in_slope=LRELU_SLOPE, prec=mma)
-                if m < n - 1:
-                    dst = bufs[m % 2]
-                    N.respair(src, c1["w"], c2["w"], c1["bias"], c2["bias"], B, Lo, Co, c1["K"], c1["d"], c2["K"],
-                              out_planes=dst, out_slope=LRELU_SLOPE, **kw)
-                    src = dst
-                else:
-                    N.respair(src, c1["w"], c2["w"], c1["bias"], c2["bias"], B, Lo, Co, c1["K"], c1["d"], c2["K"],
-                              out_f32=XS, out_accum=j > 0, **kw)
-        nxt = torch.empty_like(PA)
-        N.check(N.lib().fd_lrelu_split(N.ptr(XS), N.ptr(nxt), XS.numel(), 1.0 / nk, out_slope, pk["prec"],
-                                       N.stream_ptr(dev)), "fd_lrelu_split")
+                c1, c2 = (rb["c1f"][m], rb["c2f"][m]) if folded else (rb["c1"][m], rb["c2"][m])
+                dst = tmp[m % 2] if m < n - 1 else torch.empty_like(PA)
+                N.respair(src, c1["w"], c2["w"], c1["bias"], c2["bias"], B, Lo, Co, c1["K"], c1["d"], c2["K"],
+                          out_planes=dst, w1_inv_scale=c1["inv"], w2_inv_scale=c2["inv"], in_slope=LRELU_SLOPE,
+                          out_slope=LRELU_SLOPE, prec=mma)
+                src = dst
+            outs.append(src)
+        nxt = tmp[0]
+        N.mrf_finish(outs, nxt, in_slope=LRELU_SLOPE, scale=1.0 / nk, out_slope=out_slope, prec=pk["prec"])
         return nxt
 
     @torch.no_grad()

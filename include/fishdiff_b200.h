@@ -62,9 +62,11 @@ int fd_split_ncw(const float* src, const uint8_t* mask, uint16_t* planes, int B,
 /* fp32 [B,T,C] channels-last -> split planes; value*scale; optional row mask */
 int fd_split_nwc(const float* src, const uint8_t* mask, uint16_t* planes, int B, int T, int C, float scale,
                  int prec, void* stream);
-/* planes [2][n] = split( lrelu(src[n] * scale, slope) ): the multi-receptive-field average `xs / num_kernels`
- * followed by the LeakyReLU in front of the next upsampling stage / conv_post (models.py:420,432-434) */
-int fd_lrelu_split(const float* src, uint16_t* planes, long long n, float scale, float slope, int prec, void* stream);
+/* Multi-receptive-field average + LeakyReLU in front of the next upsampling stage / conv_post (models.py:420,426-434):
+ *   out planes [2][n] = split( lrelu( (sum_{i<num} x_i) * scale, out_slope ) ),  x_i = inverse-lrelu(in_i planes, in_slope)
+ * in[i]: planes [2][n] holding lrelu(x_i, in_slope) (the outputs of the last fused pair of each ResBlock), num <= 4. */
+int fd_mrf_finish(const uint16_t* const* in, int num, uint16_t* out, long long n, float in_slope, float scale,
+                  float out_slope, int prec, void* stream);
 /* fp32 [B,T,C] -> fp32 [B,C,T] and back (boundary transposes of the drop-in WaveNet.forward) */
 int fd_transpose_nwc_to_ncw(const float* src, float* dst, int B, int T, int C, void* stream);
 int fd_transpose_ncw_to_nwc(const float* src, float* dst, int B, int C, int T, void* stream);
@@ -139,10 +141,7 @@ int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream);
  * c1: Conv1d(C->C, k1 taps, dilation d1, 'same'), c2: Conv1d(C->C, k2 taps, dilation 1, 'same').
  * in_planes holds lrelu(x, in_slope) as split planes [2][B][T][C]; the residual x is recovered in the kernel by
  * inverting the LeakyReLU (in_slope > 0), so no fp32 master of the residual stream exists in HBM.
- * Output, exactly one of:
- *   out_planes [2][B][T][C] = split( lrelu(x', out_slope) * planes_scale )     (input of the next pair)
- *   out_f32    [B][T][C]    = x'  (out_accum = 0)  or  += x'  (out_accum = 1: the multi-receptive-field sum of
- *                             Generator.forward, models.py:426-432, accumulated by TMA reduce-add)
+ * out_planes [2][B][T][C] = split( lrelu(x', out_slope) * planes_scale )  (input of the next pair / of fd_mrf_finish).
  * w1/w2: packed weights [2][C][k*C] (tap-major K, as fd_pack_weight makes them), b1/b2 fp32 [C].
  * The c1 output lives only in shared memory; HBM traffic is 4 B/element in + 4 B/element out.
  * C in {16,32,64,128}; (k1-1)*d1 <= 56; k2 <= 17 (fd_respair_supported).  Out of place only. */
@@ -153,12 +152,10 @@ typedef struct fd_respair_desc {
   const float* b1;
   const float* b2;
   uint16_t* out_planes;
-  float* out_f32;
   int B, T, C;
   int k1, d1, k2;
   float w1_inv_scale, w2_inv_scale;
   float in_slope, out_slope, planes_scale;
-  int out_accum;
   int prec;
 } fd_respair_desc;
 int fd_respair_supported(int C, int k1, int d1, int k2);

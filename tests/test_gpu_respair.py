@@ -38,7 +38,7 @@ def make_case(B, T, C, k, d, seed):
     return x, w1, b1, w2, b2
 
 
-def run_pair(x, w1, b1, w2, b2, k, d, prec="f16", mode="planes", prev=None, out_slope=SLOPE, planes_scale=1.0):
+def run_pair(x, w1, b1, w2, b2, k, d, prec="f16", out_slope=SLOPE, planes_scale=1.0):
     pc = N.prec_code(prec)
     B, T, C = x.shape
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev())
@@ -46,14 +46,10 @@ def run_pair(x, w1, b1, w2, b2, k, d, prec="f16", mode="planes", prev=None, out_
     pa = N.split_nwc(torch.where(xin >= 0, xin, xin * SLOPE), pc)
     s1, s2 = N.pow2_scale(t(w1)), N.pow2_scale(t(w2))
     w1p, w2p = N.pack_weight(t(w1), pc, s1), N.pack_weight(t(w2), pc, s2)
-    kw = dict(w1_inv_scale=1.0 / s1, w2_inv_scale=1.0 / s2, in_slope=SLOPE, out_slope=out_slope,
-              planes_scale=planes_scale, prec=N.mma_code(prec))
-    if mode == "planes":
-        out = torch.zeros((2, B, T, C), dtype=torch.int16, device=dev())
-        N.respair(pa, w1p, w2p, t(b1), t(b2), B, T, C, k, d, k, out_planes=out, **kw)
-    else:
-        out = torch.full((B, T, C), 3.0, dtype=torch.float32, device=dev()) if prev is None else t(prev)
-        N.respair(pa, w1p, w2p, t(b1), t(b2), B, T, C, k, d, k, out_f32=out, out_accum=mode == "accum", **kw)
+    out = torch.zeros((2, B, T, C), dtype=torch.int16, device=dev())
+    N.respair(pa, w1p, w2p, t(b1), t(b2), B, T, C, k, d, k, out_planes=out, w1_inv_scale=1.0 / s1,
+              w2_inv_scale=1.0 / s2, in_slope=SLOPE, out_slope=out_slope, planes_scale=planes_scale,
+              prec=N.mma_code(prec))
     torch.cuda.synchronize()
     ref = pair_ref(planes_to_f64(pa, pc), planes_to_f64(w1p, pc) / s1, b1.astype(np.float64),
                    planes_to_f64(w2p, pc) / s2, b2.astype(np.float64), k, d, k)
@@ -77,21 +73,22 @@ def test_pair_planes_out(C, kd):
     assert rel_l2(got, want) < 1e-5, (rel_l2(got, want), np.abs(got - want).max())   # measured <= 4e-6 (K up to 1408, two chained convs)
 
 
-@pytest.mark.parametrize("C", [16, 32, 64, 128])
-def test_pair_f32_store_and_accumulate(C):
-    k, d = 7, 3
-    B, T = 3, 257
-    x, w1, b1, w2, b2 = make_case(B, T, C, k, d, 7 + C)
-    out, ref, _ = run_pair(x, w1, b1, w2, b2, k, d, mode="store")
-    assert rel_l2(out.cpu().numpy(), ref) < 1e-5
-    prev = np.random.RandomState(5).randn(B, T, C).astype(np.float32)
-    out, ref, _ = run_pair(x, w1, b1, w2, b2, k, d, mode="accum", prev=prev)
-    assert rel_l2(out.cpu().numpy(), ref + prev) < 1e-5
+def test_mrf_finish():
+    """fd_mrf_finish: lrelu(mean_i invlrelu(p_i)) on plane tensors (models.py:426-434)."""
+    rng = np.random.RandomState(2)
+    xs = [torch.from_numpy(rng.randn(3, 50, 16).astype(np.float32)).to(dev()) for _ in range(3)]
+    ps = [N.split_nwc(torch.where(x >= 0, x, x * SLOPE), N.PREC_F16) for x in xs]
+    out = torch.empty_like(ps[0])
+    N.mrf_finish(ps, out, in_slope=SLOPE, scale=1.0 / 3, out_slope=0.01)
+    torch.cuda.synchronize()
+    vals = [planes_to_f64(p, N.PREC_F16) for p in ps]
+    want = lrelu(sum(np.where(v >= 0, v, v / SLOPE) for v in vals) / 3, 0.01)
+    assert rel_l2(planes_to_f64(out, N.PREC_F16), want) < 1e-6
 
 
-@pytest.mark.parametrize("T", [1, 5, 117, 118, 119, 128, 1000])
+@pytest.mark.parametrize("T", [1, 5, 245, 246, 247, 256, 1000])
 def test_pair_ragged_lengths(T):
-    C, k, d = 64, 11, 5                 # r_out = 118: items shorter than / equal to / just above one tile
+    C, k, d = 64, 11, 5                 # r_out = 2*128 - 10 = 246: items shorter than / equal to / just above one tile
     x, w1, b1, w2, b2 = make_case(2, T, C, k, d, T)
     out, ref, pc = run_pair(x, w1, b1, w2, b2, k, d)
     assert rel_l2(planes_to_f64(out, pc), lrelu(ref)) < 1e-5
