@@ -29,6 +29,15 @@
 #include "fd_host.h"
 #include "fd_tc_ptx.cuh"
 
+// epilogue warps: 16 at C = 128 (one block per tile: more warps hide the TMEM / shared-memory latencies of the one
+// non-overlapped epilogue; measured 16.1 -> 15.1 ms for k = 11), 8 below (measured slower with 16: 3.13 -> 3.9 ms)
+#ifndef FD_RP_EPI_WARPS
+#define FD_RP_EPI_WARPS(C) ((C) >= 128 ? 16 : 8)
+#endif
+#ifndef FD_RP_STAGE_MAJOR
+#define FD_RP_STAGE_MAJOR(C) ((C) == 64 || (C) == 32)
+#endif
+
 namespace {
 
 struct FdResPairK {
@@ -74,9 +83,15 @@ struct RpCfg {
   static constexpr int MID_PLANE_BYTES = MID_ROWS * ROWB;
   static constexpr int MID_KB_BYTES = 2 * MID_PLANE_BYTES;
   static constexpr int MID_BYTES = NKB * MID_KB_BYTES;     // c1 output; afterwards the staging image of the output
-  static constexpr int EPI_WARPS = 8;
-  static constexpr int GROUPS = C == 16 ? 2 : 1;            // warp groups taking alternate blocks
-  static constexpr int HALVES = C == 16 ? 1 : 2;            // warp groups splitting the columns of one block
+  // STAGE_MAJOR: every weight stage is used by all MB blocks of the tile before it is released, so the pair's weights
+  // stream through L2 -> shared memory once per tile instead of once per block (the weight stream is what bounds
+  // C = 32 / 64); the price is that the blocks of a tile finish a GEMM together, so their epilogues no longer overlap
+  // the MMAs of the following blocks.
+  static constexpr bool STAGE_MAJOR = FD_RP_STAGE_MAJOR(C);
+  static constexpr int EPI_WARPS = FD_RP_EPI_WARPS(C);
+  static constexpr int HALVES_WANT = C >= 128 ? 4 : C >= 32 ? 2 : 1;
+  static constexpr int HALVES = HALVES_WANT > EPI_WARPS / 4 ? EPI_WARPS / 4 : HALVES_WANT;   // column split of a block
+  static constexpr int GROUPS = EPI_WARPS / 4 / HALVES;     // warp groups taking alternate blocks
   static constexpr int COLS = C / HALVES;                   // columns per epilogue thread
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int GTHREADS = EPI_THREADS / GROUPS;
@@ -197,7 +212,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         for (int g2 = 0; g2 < 2; ++g2) {
           const CUtensorMap* tm = g2 == 0 ? &tm_w1 : &tm_w2;
           const int units = g2 == 0 ? units1 : units2;
-          for (int j = 0; j < MB; ++j) {
+          for (int j = 0; j < (K::STAGE_MAJOR ? 1 : MB); ++j) {
             for (int u0 = 0; u0 < units; u0 += K::GROUP) {
               const int nb = min(K::GROUP, units - u0);
               mbar_wait(&w_empty[stage], phase ^ 1);
@@ -254,6 +269,56 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const uint32_t a_plane = g2 == 0 ? (uint32_t)K::IN_PLANE_BYTES : (uint32_t)K::MID_PLANE_BYTES;
         const uint32_t tap_bytes = (uint32_t)(g2 == 0 ? p.d1 : 1) * K::ROWB;
         if (g2 == 0) { mbar_wait(in_full, it & 1); tc_fence_after(); }
+        if (K::STAGE_MAJOR) {
+          if (g2 == 1) {   // every block's mid rows and residual-initialised accumulator
+#pragma unroll 1
+            for (int j = 0; j < MB; ++j) mbar_wait(&mid_ready[j], it & 1);
+            tc_fence_after();
+          }
+          int u = 0;
+#pragma unroll 1
+          for (int u0 = 0; u0 < units; u0 += K::GROUP) {
+            const int nb = min(K::GROUP, units - u0);
+            mbar_wait(&w_full[stage], phase);
+            tc_fence_after();
+            const uint32_t w_stage = smem_u32(w_s + stage * K::STAGE_BYTES);
+#pragma unroll 1
+            for (int g = 0; g < nb; ++g, ++u) {
+              const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
+              const int ch = kw * K::BKW;
+              const uint32_t a0 = a_base + (ch / K::BK_A) * a_kb + (uint32_t)tap * tap_bytes + (ch % K::BK_A) * 2;
+              const uint64_t dw = DESC_HI_W | (uint64_t)(((w_stage + g * K::UNIT_BYTES) & 0x3FFFF) >> 4);
+              const uint32_t first = (g2 == 1 || u != 0) ? 1u : 0u;
+              if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < MB; ++j) {
+                  const uint32_t d_tmem = (g2 == 0 ? acc1 : acc2) + j * 2 * C;
+                  const uint32_t a_hi = a0 + (uint32_t)(j * 128) * K::ROWB;
+                  const uint64_t da_hi = DESC_HI_A | (uint64_t)((a_hi & 0x3FFFF) >> 4);
+                  const uint64_t da_lo = DESC_HI_A | (uint64_t)(((a_hi + a_plane) & 0x3FFFF) >> 4);
+#pragma unroll
+                  for (int k = 0; k < K::BKW / 16; ++k) {
+                    const uint32_t accum = (k != 0) ? 1u : first;
+                    if (!single) {
+                      umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_2c, accum);
+                      umma_f16(d_tmem, da_lo + 2 * k, dw + 2 * k, idesc_c, 1u);
+                    } else {
+                      umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_c, accum);
+                    }
+                  }
+                }
+              }
+              __syncwarp();
+            }
+            if (elect_one()) umma_commit(&w_empty[stage]);
+            __syncwarp();
+            if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (elect_one()) {
+            for (int j = 0; j < MB; ++j) umma_commit(g2 == 0 ? &acc1_full[j] : &acc2_full[j]);
+          }
+          __syncwarp();
+        } else {
 #pragma unroll 1
         for (int j = 0; j < MB; ++j) {
           const uint32_t d_tmem = (g2 == 0 ? acc1 : acc2) + j * 2 * C;
@@ -299,14 +364,15 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           if (elect_one()) umma_commit(g2 == 0 ? &acc1_full[j] : &acc2_full[j]);
           __syncwarp();
         }
+        }
       }
     }
   } else if (warp >= 4) {
     // =========================================================== epilogue
     const int q = warp % 4;
     const int wg = (warp - 4) / 4;
-    const int grp = K::GROUPS == 2 ? wg : 0;          // which blocks this warp takes (j % GROUPS == grp)
-    const int half = K::HALVES == 2 ? wg : 0;         // which columns of a block
+    const int grp = wg / K::HALVES;                   // which blocks this warp takes (j % GROUPS == grp)
+    const int half = wg % K::HALVES;                  // which columns of a block
     const int row = q * 32 + lane;
     const int col_base = half * K::COLS;
     const int etid = threadIdx.x - 128;
@@ -326,7 +392,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           mbar_wait(in_full, it & 1);                  // visibility of the TMA-written input tile to these threads
           // the staging image (= mid tile) of the previous tile must have been read by its TMA stores
           if (issuer) bulk_wait_read0();
-          asm volatile("bar.sync 3, %0;" ::"r"(K::EPI_THREADS) : "memory");
+          asm volatile("bar.sync 8, %0;" ::"r"(K::EPI_THREADS) : "memory");
         }
         const int m = j * 128 + row;                   // row of the mid tile
         // (a) residual + c2 bias -> accumulator 2 (pre-scaled by the weight prescale of c2), zeros in the [w_lo] half
