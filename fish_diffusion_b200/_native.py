@@ -63,6 +63,25 @@ class ResPairDesc(ctypes.Structure):
     ]
 
 
+class WaveNetFwdDesc(ctypes.Structure):
+    """struct fd_wavenet_fwd_desc (include/fishdiff_b200.h)."""
+    _fields_ = [
+        ("x_planes", c_void_p), ("cond_planes", c_void_p), ("steps", c_void_p), ("x_mask", c_void_p), ("out", c_void_p),
+        ("w_in", c_void_p), ("b_in", c_void_p), ("w_in_inv", c_float),
+        ("mlp_w0", c_void_p), ("mlp_b0", c_void_p), ("mlp_w1", c_void_p), ("mlp_b1", c_void_p),
+        ("wd", c_void_p), ("bd", c_void_p), ("w1p_f32", c_void_p), ("bias_sum", c_void_p),
+        ("w1", c_void_p), ("w1_lstride", c_longlong), ("w2", c_void_p), ("w2_lstride", c_longlong),
+        ("b2", c_void_p), ("b2_lstride", c_longlong),
+        ("w_skip", c_void_p), ("b_skip", c_void_p), ("w_skip_inv", c_float),
+        ("w_out", c_void_p), ("b_out", c_void_p), ("w_out_inv", c_float),
+        ("w1_inv", c_float * 64), ("w2_inv", c_float * 64), ("dilation", c_int * 64),
+        ("xr", c_void_p), ("z", c_void_p), ("skip_planes", c_void_p), ("skip_f32", c_void_p),
+        ("s", c_void_p), ("mlp_ws", c_void_p), ("gb", c_void_p), ("gb_ws", c_void_p),
+        ("B", c_int), ("T", c_int), ("M", c_int), ("C", c_int), ("E", c_int), ("L", c_int), ("Bs", c_int),
+        ("gate_tile", c_int), ("prec", c_int), ("backend", c_int),
+    ]
+
+
 class WgradDesc(ctypes.Structure):
     """struct fd_wgrad_desc (include/fishdiff_b200.h)."""
     _fields_ = [
@@ -105,6 +124,7 @@ _SIGS = {
     "fd_wavenet_gate_bias": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_void_p]),
     "fd_wavenet_block_fwd": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p, c_void_p, c_float] + [c_int] * 6 +
                              [c_float, c_float, c_int, c_int, c_int, c_void_p]),
+    "fd_wavenet_fwd": (c_int, [POINTER(WaveNetFwdDesc), c_void_p]),
     "fd_conv_cl_fwd": (c_int, [POINTER(ConvDesc), c_void_p]),
     "fd_respair_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "fd_respair_fwd": (c_int, [POINTER(ResPairDesc), c_void_p]),
@@ -301,8 +321,19 @@ PROF_KINDS = {0: "linear/tc", 1: "linear/simt", 2: "gate/tc", 3: "gate/simt", 4:
               6: "mag/tc", 7: "mag/simt"}
 
 
+_prof_on = False
+
+
 def prof_enable(on: bool):
+    """Per-launch CUDA-event timing of the tap-GEMM kernels.  While it is on, CUDA-graph replay of the denoiser is
+    disabled (events recorded inside a captured graph cannot be timed)."""
+    global _prof_on
+    _prof_on = bool(on)
     lib().fd_prof_enable(1 if on else 0)
+
+
+def prof_is_on() -> bool:
+    return _prof_on
 
 
 def prof_collect():

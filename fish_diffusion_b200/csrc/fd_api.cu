@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include "fd_common.cuh"
 #include "fd_host.h"
@@ -206,6 +207,51 @@ static int wavenet_block(const uint16_t* x_planes, uint16_t* x_out_planes, const
   q.x_planes = const_cast<uint16_t*>(x_planes); q.x_out_planes = x_out_planes; q.skip_f32 = skip_f32; q.skip_planes = skip_planes; q.skip_scale = skip_scale;
   q.first_layer = flags & 1; q.last_layer = (flags >> 1) & 1; q.C = C;
   return run(q, backend, st);
+}
+
+int fd_wavenet_fwd(const fd_wavenet_fwd_desc* d, void* stream) {
+  FD_DEVICE_GUARD();
+  FD_REQUIRE(d != nullptr, "fd_wavenet_fwd: null descriptor");
+  FD_REQUIRE(d->L >= 1 && d->L <= 64, "fd_wavenet_fwd: L=%d out of range (1..64)", d->L);
+  FD_REQUIRE(d->Bs == 1 || d->Bs == d->B, "fd_wavenet_fwd: Bs=%d must be 1 or B=%d", d->Bs, d->B);
+  const int B = d->B, T = d->T, M = d->M, C = d->C, E = d->E, L = d->L, Bs = d->Bs;
+  int rc = fd_wavenet_step_mlp(d->steps, d->mlp_w0, d->mlp_b0, d->mlp_w1, d->mlp_b1, d->s, d->mlp_ws, Bs, C, stream);
+  if (rc) return rc;
+  float* gb_full = d->gb;
+  float* gb_lo = d->gb + (size_t)L * Bs * 2 * C;
+  float* gb_hi = d->gb + (size_t)2 * L * Bs * 2 * C;
+  rc = fd_wavenet_gate_bias(d->s, d->wd, d->bd, d->w1p_f32, d->bias_sum, gb_full, gb_lo, gb_hi, d->gb_ws, L, Bs, C,
+                            3 * C + E, stream);
+  if (rc) return rc;
+  fd_conv_desc cd;
+  memset(&cd, 0, sizeof(cd));
+  cd.B = B; cd.T = T; cd.ntaps = 1; cd.shifts[0] = 0;
+  cd.post_scale = 1.f; cd.planes_scale = 1.f; cd.prec = d->prec; cd.backend = d->backend;
+  // head: relu(input_projection(x)), masked rows zeroed (wavenet.py:211-218)
+  cd.in_planes = d->x_planes; cd.w_planes = d->w_in; cd.bias = d->b_in; cd.row_mask = d->x_mask;
+  cd.out_planes = d->xr; cd.Cin = M; cd.N = C; cd.w_inv_scale = d->w_in_inv; cd.act = 1;
+  rc = fd_conv_cl_fwd(&cd, stream);
+  if (rc) return rc;
+  const int gb_stride = Bs > 1 ? 2 * C : 0;
+  const float skip_scale = 1.f / sqrtf((float)L);
+  for (int l = 0; l < L; ++l) {
+    const int flags = (l == 0 ? 1 : 0) | (l == L - 1 ? 2 : 0);
+    const size_t go = (size_t)l * Bs * 2 * C;
+    rc = fd_wavenet_block_fwd(d->xr, d->cond_planes, d->z, d->w1 + (size_t)l * d->w1_lstride,
+                              d->w2 + (size_t)l * d->w2_lstride, gb_full + go, gb_lo + go, gb_hi + go, gb_stride,
+                              d->b2 + (size_t)l * d->b2_lstride, d->skip_f32, d->skip_planes, skip_scale, B, T, C, E,
+                              d->dilation[l], d->gate_tile, d->w1_inv[l], d->w2_inv[l], flags, d->prec, d->backend,
+                              stream);
+    if (rc) return rc;
+  }
+  // tail: relu(skip_projection(sum / sqrt(L))) -> output_projection, masked rows zeroed (wavenet.py:228-234)
+  cd.in_planes = d->skip_planes; cd.w_planes = d->w_skip; cd.bias = d->b_skip; cd.row_mask = nullptr;
+  cd.out_planes = d->z; cd.out_f32 = nullptr; cd.Cin = C; cd.N = C; cd.w_inv_scale = d->w_skip_inv; cd.act = 1;
+  rc = fd_conv_cl_fwd(&cd, stream);
+  if (rc) return rc;
+  cd.in_planes = d->z; cd.w_planes = d->w_out; cd.bias = d->b_out; cd.row_mask = d->x_mask;
+  cd.out_planes = nullptr; cd.out_f32 = d->out; cd.Cin = C; cd.N = M; cd.w_inv_scale = d->w_out_inv; cd.act = 0;
+  return fd_conv_cl_fwd(&cd, stream);
 }
 
 int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream) {

@@ -338,10 +338,21 @@ class GaussianDiffusion(nn.Module):
             it = tqdm(chunks)
         eps = torch.empty((B, T, M), dtype=torch.float32, device=dev)
         seed = self._rng_seed()
+        # converted once per call: the denoiser replays a captured CUDA graph when it sees the same buffers again
+        if x_masks is not None:
+            x_masks = x_masks.to(device=dev, dtype=torch.uint8).contiguous()
+        step_table = {}      # diffusion step (float) -> 1-element device tensor, uploaded once per sampler call
 
         def denoise(xp, t_float, masks=True, out=eps):
-            steps = torch.tensor([t_float], dtype=torch.float32, device=dev)
+            steps = step_table.get(t_float)
+            if steps is None:
+                steps = step_table[t_float] = torch.tensor([t_float], dtype=torch.float32, device=dev)
             return den.forward_cl(xp, steps, cond_planes, x_mask=x_masks if masks else None, out=out)
+
+        if noise_predictor in ("naive", "plms") and len(chunks) > 1:   # one upload for the whole schedule
+            tab = torch.tensor([float(t) for t in chunks], dtype=torch.float32, device=dev)
+            for i, t in enumerate(chunks):
+                step_table[float(t)] = tab[i:i + 1]
 
         if noise_predictor == "naive":
             for i, t in enumerate(it):

@@ -11,6 +11,7 @@ Data flow of one call (all activations channels-last split planes, see csrc/fd_c
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 
@@ -116,6 +117,9 @@ class WaveNet(nn.Module):
         self._scale_state = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_scale_state", None))
         self._ws = {}
+        self._graphs = {}
+        # CUDA-graph replay of repeated evaluations on the same buffers (the sampler loop); FD_GRAPH=0 disables it
+        self.use_graph = os.environ.get("FD_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------------------------------ packing
     def _resolve_backend(self) -> int:
@@ -262,8 +266,10 @@ class WaveNet(nn.Module):
                 "skip_planes": torch.empty((2, B, T, C), **i16), "skip_f32": torch.empty((B, T, C), **f32),
                 "s": torch.empty((Bs, C), **f32), "mlp_ws": torch.empty((Bs * 5 * C,), **f32),
                 "gb": torch.empty((3, L, Bs, 2 * C), **f32), "gb_ws": torch.empty((L * Bs * C,), **f32),
+                "steps": torch.empty((Bs,), **f32),
             }
             self._ws = {key: ws}   # keep one shape resident
+            self._graphs = {}      # captured evaluations reference the old workspace
         return ws
 
     # ------------------------------------------------------------------------------------ training path
@@ -344,31 +350,57 @@ class WaveNet(nn.Module):
         if out is None:
             out = torch.empty((B, T, M), dtype=torch.float32, device=dev)
 
-        N.check(lib.fd_wavenet_step_mlp(N.ptr(steps), N.ptr(pk["mlp_w0"]), N.ptr(pk["mlp_b0"]), N.ptr(pk["mlp_w1"]),
-                                        N.ptr(pk["mlp_b1"]), N.ptr(ws["s"]), N.ptr(ws["mlp_ws"]), Bs, C, st),
-                "fd_wavenet_step_mlp")
-        gb = ws["gb"]
-        N.check(lib.fd_wavenet_gate_bias(N.ptr(ws["s"]), N.ptr(pk["wd"]), N.ptr(pk["bd"]), N.ptr(pk["w1p_f32"]),
-                                         N.ptr(pk["bias_sum"]), N.ptr(gb[0]), N.ptr(gb[1]), N.ptr(gb[2]),
-                                         N.ptr(ws["gb_ws"]), L, Bs, C, 3 * C + E, st), "fd_wavenet_gate_bias")
-        # head: relu(input_projection(x)) with masked rows zeroed (wavenet.py:211-218)
-        N.conv_cl(x_planes, pk["w_in"], B, T, M, C, [0], bias=pk["b_in"], row_mask=x_mask, out_planes=ws["xr"],
-                  w_inv_scale=pk["w_in_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
-        gb_stride = 2 * C if Bs > 1 else 0
-        skip_scale = 1.0 / math.sqrt(L)
-        for l in range(L):
-            flags = (1 if l == 0 else 0) | (2 if l == L - 1 else 0)
-            N.check(lib.fd_wavenet_block_fwd(
-                N.ptr(ws["xr"]), N.ptr(cond_planes), N.ptr(ws["z"]), N.ptr(pk["w1"][l]), N.ptr(pk["w2"][l]),
-                N.ptr(gb[0, l]), N.ptr(gb[1, l]), N.ptr(gb[2, l]), gb_stride, N.ptr(pk["b2"][l]),
-                N.ptr(ws["skip_f32"]), N.ptr(ws["skip_planes"]), skip_scale, B, T, C, E, pk["dil"][l],
-                pk["gate_tile"], pk["w1_inv"][l], pk["w2_inv"][l], flags, mma, backend, st), "fd_wavenet_block_fwd")
-        # tail: relu(skip_projection(sum/sqrt(L))) -> output_projection (+ mask) (wavenet.py:228-234)
-        N.conv_cl(ws["skip_planes"], pk["w_skip"], B, T, C, C, [0], bias=pk["b_skip"], out_planes=ws["z"],
-                  w_inv_scale=pk["w_skip_inv"], act=N.ACT_RELU, prec=mma, backend=backend)
-        N.conv_cl(ws["z"], pk["w_out"], B, T, C, M, [0], bias=pk["b_out"], row_mask=x_mask, out_f32=out,
-                  w_inv_scale=pk["w_out_inv"], prec=mma, backend=backend)
+        # ONE native call per evaluation (fd_wavenet_fwd issues the ~45 launches back to back); when the same buffers
+        # come back (the sampler loop) the call is captured into a CUDA graph on its second use and replayed afterwards,
+        # which also removes the per-launch tensor-map encodes from the host path.
+        steps_buf = ws["steps"]
+        steps_buf.copy_(steps, non_blocking=True)
+        d = self._fwd_desc(pk, ws, x_planes, cond_planes, steps_buf, x_mask, out, B, T, Bs)
+        use_graph = self.use_graph and not N.prof_is_on()
+        if not use_graph:
+            N.check(lib.fd_wavenet_fwd(ctypes.byref(d), st), "fd_wavenet_fwd")
+            return out
+        key = (x_planes.data_ptr(), cond_planes.data_ptr(), out.data_ptr(), 0 if x_mask is None else x_mask.data_ptr(),
+               B, T, Bs, self._pack_key, id(ws))
+        ent = self._graphs.get(key)
+        if ent is None:                      # first sight of these buffers: run eagerly (lazy inits happen here)
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            self._graphs[key] = {"graph": None, "keep": (x_planes, cond_planes, out, x_mask, pk)}
+            N.check(lib.fd_wavenet_fwd(ctypes.byref(d), st), "fd_wavenet_fwd")
+            return out
+        if ent["graph"] is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                N.check(lib.fd_wavenet_fwd(ctypes.byref(d), N.stream_ptr(dev)), "fd_wavenet_fwd")
+            ent["graph"] = g
+        ent["graph"].replay()
         return out
+
+    def _fwd_desc(self, pk, ws, x_planes, cond_planes, steps, x_mask, out, B, T, Bs):
+        C, E, M, L = self.residual_channels, self.d_encoder, self.mel_channels, self.n_layers
+        if L > 64:
+            raise ValueError("fd_wavenet_fwd supports up to 64 residual layers")
+        d = N.WaveNetFwdDesc()
+        d.x_planes, d.cond_planes, d.steps, d.x_mask, d.out = (N.ptr(x_planes), N.ptr(cond_planes), N.ptr(steps),
+                                                               N.ptr(x_mask), N.ptr(out))
+        d.w_in, d.b_in, d.w_in_inv = N.ptr(pk["w_in"]), N.ptr(pk["b_in"]), pk["w_in_inv"]
+        d.mlp_w0, d.mlp_b0, d.mlp_w1, d.mlp_b1 = (N.ptr(pk["mlp_w0"]), N.ptr(pk["mlp_b0"]), N.ptr(pk["mlp_w1"]),
+                                                  N.ptr(pk["mlp_b1"]))
+        d.wd, d.bd, d.w1p_f32, d.bias_sum = N.ptr(pk["wd"]), N.ptr(pk["bd"]), N.ptr(pk["w1p_f32"]), N.ptr(pk["bias_sum"])
+        w1s, w2s = self._pack_static["w1"], self._pack_static["w2"]
+        d.w1, d.w1_lstride = N.ptr(w1s), w1s.stride(0)
+        d.w2, d.w2_lstride = N.ptr(w2s), w2s.stride(0)
+        d.b2, d.b2_lstride = N.ptr(pk["b2"]), pk["b2"].stride(0)
+        d.w_skip, d.b_skip, d.w_skip_inv = N.ptr(pk["w_skip"]), N.ptr(pk["b_skip"]), pk["w_skip_inv"]
+        d.w_out, d.b_out, d.w_out_inv = N.ptr(pk["w_out"]), N.ptr(pk["b_out"]), pk["w_out_inv"]
+        for l in range(L):
+            d.w1_inv[l], d.w2_inv[l], d.dilation[l] = pk["w1_inv"][l], pk["w2_inv"][l], pk["dil"][l]
+        d.xr, d.z, d.skip_planes, d.skip_f32 = N.ptr(ws["xr"]), N.ptr(ws["z"]), N.ptr(ws["skip_planes"]), N.ptr(ws["skip_f32"])
+        d.s, d.mlp_ws, d.gb, d.gb_ws = N.ptr(ws["s"]), N.ptr(ws["mlp_ws"]), N.ptr(ws["gb"]), N.ptr(ws["gb_ws"])
+        d.B, d.T, d.M, d.C, d.E, d.L, d.Bs = B, T, M, C, E, L, Bs
+        d.gate_tile, d.prec, d.backend = pk["gate_tile"], pk["mma"], pk["backend"]
+        return d
 
     def forward(self, x, diffusion_step, conditioner, x_masks=None, cond_masks=None):
         """Reference contract (wavenet.py:194-236): x [B,M,T] (or [B,1,M,T]), diffusion_step [B] or [1] (int64 or

@@ -96,6 +96,37 @@ int fd_wavenet_step_mlp(const float* steps, const float* w0, const float* b0, co
 int fd_wavenet_gate_bias(const float* s, const float* wd, const float* bd, const float* w1p, const float* bias_sum,
                          float* gb_full, float* gb_lo, float* gb_hi, float* ws, int L, int Bs, int C, int KT,
                          void* stream);
+/* One complete WaveNet.forward (wavenet.py:194-236) on channels-last split planes as ONE native call: step MLP,
+ * gate-bias tables, input projection, L residual blocks, skip / output projections -- the launches of
+ * fd_wavenet_step_mlp, fd_wavenet_gate_bias, fd_conv_cl_fwd and L x fd_wavenet_block_fwd issued back to back on
+ * `stream` (capturable into a CUDA graph: nothing here synchronises or allocates).  Replaces the per-layer Python loop of
+ * the reference (`for layer in self.residual_layers`, wavenet.py:223-226) and its ~245 kernel launches per call.
+ * Host arrays: w1_inv / w2_inv / dilation [L].  w1 / w2 / b2 are [L] stacks with the given element strides. */
+typedef struct fd_wavenet_fwd_desc {
+  const uint16_t* x_planes;     /* [2][B][T][M] */
+  const uint16_t* cond_planes;  /* [2][B][T][E] */
+  const float* steps;           /* [Bs] diffusion steps (float), Bs = 1 or B */
+  const uint8_t* x_mask;        /* [B][T] or NULL (wavenet.py:217-218, 233-234) */
+  float* out;                   /* eps fp32 [B][T][M] */
+  /* packed weights (WaveNet._packed) */
+  const uint16_t* w_in; const float* b_in; float w_in_inv;
+  const float* mlp_w0; const float* mlp_b0; const float* mlp_w1; const float* mlp_b1;
+  const float* wd; const float* bd; const float* w1p_f32; const float* bias_sum;
+  const uint16_t* w1; long long w1_lstride;
+  const uint16_t* w2; long long w2_lstride;
+  const float* b2; long long b2_lstride;
+  const uint16_t* w_skip; const float* b_skip; float w_skip_inv;
+  const uint16_t* w_out; const float* b_out; float w_out_inv;
+  float w1_inv[64], w2_inv[64];
+  int dilation[64];
+  /* workspace (caller-owned, see WaveNet._workspace) */
+  uint16_t* xr; uint16_t* z; uint16_t* skip_planes; float* skip_f32;
+  float* s; float* mlp_ws; float* gb; float* gb_ws;
+  int B, T, M, C, E, L, Bs;
+  int gate_tile, prec, backend;
+} fd_wavenet_fwd_desc;
+int fd_wavenet_fwd(const fd_wavenet_fwd_desc* d, void* stream);
+
 /* One ResidualBlock.forward (wavenet.py:106-120), fused as two tap-GEMM launches:
  *   GEMM1  y = [W_conv(3 taps) | W_cond] . [x(t-d), x(t), x(t+d), cond(t)] + gate bias ; z = sigmoid(y_g)*tanh(y_f)
  *   GEMM2  o = W_out z + b ;  x <- (x + o_res)/sqrt(2) (in place) ;  skip_acc (+)= o_skip

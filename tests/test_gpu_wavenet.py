@@ -82,8 +82,8 @@ def test_wavenet_repacks_when_weights_change(golden_cfg):
 
 
 def test_reference_layout_forward_is_differentiable(golden_cfg):
-    """WaveNet.forward([B,M,T]) with grad enabled goes through the native backward (never silently detached);
-    masks are refused there because the reference trains without them (diffusion.py:134)."""
+    """WaveNet.forward([B,M,T]) with grad enabled goes through the native backward (never silently detached): gradients
+    reach the parameters, the conditioner AND x; masks act as in the reference forward (wavenet.py:217-221,233-234)."""
     cfg = golden_cfg["WN_TC"]
     net = build_net(cfg, wn_weights(1, cfg))
     x = torch.randn(1, 64, 20, device=dev())
@@ -96,8 +96,19 @@ def test_reference_layout_forward_is_differentiable(golden_cfg):
     with torch.no_grad():
         y0 = net(x, torch.tensor([1], device=dev()), c)
     assert torch.allclose(y0, y.detach(), rtol=1e-5, atol=1e-6)      # training and inference forwards agree
-    with pytest.raises(NotImplementedError):
-        net(x, torch.tensor([1], device=dev()), c, x_masks=torch.zeros(1, 20, dtype=torch.bool, device=dev()))
+    # masks under grad: same values as the masked inference forward, zero gradient into masked conditioner rows
+    m = torch.zeros(1, 20, dtype=torch.bool, device=dev())
+    m[0, 13:] = True
+    xg = x.clone().requires_grad_(True)
+    c2 = c.detach().clone().requires_grad_(True)
+    ym = net(xg, torch.tensor([1], device=dev()), c2, x_masks=m, cond_masks=m)
+    with torch.no_grad():
+        ym0 = net(x, torch.tensor([1], device=dev()), c, x_masks=m, cond_masks=m)
+    assert torch.allclose(ym0, ym.detach(), rtol=1e-5, atol=1e-6)
+    assert float(ym.detach()[0, :, 13:].abs().max()) == 0.0
+    ym.square().mean().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all() and float(xg.grad.abs().max()) > 0
+    assert float(c2.grad[0, :, 13:].abs().max()) == 0.0 and float(c2.grad[0, :, :13].abs().max()) > 0
 
 
 # ------------------------------------------------------------------ samplers, noise injected
