@@ -318,7 +318,7 @@ def mrf_finish(ins, out, *, in_slope=0.1, scale=1.0, out_slope=0.1, prec=PREC_F1
 
 
 PROF_KINDS = {0: "linear/tc", 1: "linear/simt", 2: "gate/tc", 3: "gate/simt", 4: "res_skip/tc", 5: "res_skip/simt",
-              6: "mag/tc", 7: "mag/simt"}
+              6: "mag/tc", 7: "mag/simt", 8: "respair/128", 9: "respair/64", 10: "respair/32", 11: "respair/16"}
 
 
 _prof_on = False

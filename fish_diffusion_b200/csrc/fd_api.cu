@@ -29,7 +29,9 @@ int g_prof_n = 0;
 cudaEvent_t* g_prof_ev = nullptr;   // 2 * PROF_MAX events, created lazily
 int g_prof_kind[PROF_MAX];
 
-void prof_begin(int kind, cudaStream_t st) {
+}  // namespace
+
+void fd_prof_begin(int kind, cudaStream_t st) {
   if (!g_prof_on || g_prof_n >= PROF_MAX) return;
   if (g_prof_ev == nullptr) {
     g_prof_ev = new cudaEvent_t[2 * PROF_MAX];
@@ -42,15 +44,17 @@ void prof_begin(int kind, cudaStream_t st) {
   g_prof_kind[g_prof_n] = kind;
   cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
 }
-void prof_end(cudaStream_t st) {
+void fd_prof_end(cudaStream_t st) {
   if (!g_prof_on || g_prof_n >= PROF_MAX) return;
   cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st);
   ++g_prof_n;
 }
 
+namespace {
+
 int run(const FdTapGemm& p, int backend, cudaStream_t st) {
   int rc;
-  prof_begin(p.epi * 2 + (backend == FD_BACKEND_TC ? 0 : 1), st);
+  fd_prof_begin(p.epi * 2 + (backend == FD_BACKEND_TC ? 0 : 1), st);
   if (backend == FD_BACKEND_TC) {
     rc = fd_tapgemm_tc_launch(p, st);
   } else if (backend == FD_BACKEND_SIMT) {
@@ -59,7 +63,7 @@ int run(const FdTapGemm& p, int backend, cudaStream_t st) {
     fd_set_error("unknown backend %d", backend);
     return -2;
   }
-  prof_end(st);
+  fd_prof_end(st);
   if (rc == 0) fd_count_launch(1);
   return rc;
 }

@@ -5,6 +5,9 @@
 
 extern "C" void fd_set_error(const char* fmt, ...);
 void fd_count_launch(int n);
+// per-launch device timing (fd_prof_enable): event pair around a launch; kind indexes fd_prof_collect's arrays
+void fd_prof_begin(int kind, cudaStream_t st);
+void fd_prof_end(cudaStream_t st);
 
 // call right after a kernel launch inside an `int`-returning API function
 #define FD_LAUNCHED()                                                                          \

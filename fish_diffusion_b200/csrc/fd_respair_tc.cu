@@ -597,7 +597,9 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   }
   const int tiles = p.B * ((p.T + p.r_out - 1) / p.r_out);
   const int sms = fd_device_sms(dev);
+  fd_prof_begin(C == 128 ? 8 : C == 64 ? 9 : C == 32 ? 10 : 11, stream);
   kern<<<tiles < sms ? tiles : sms, K::THREADS, K::SMEM_BYTES, stream>>>(tin, tw1, tw2, tout, tout_last, p);
+  fd_prof_end(stream);
   FD_CHECK_CUDA(cudaGetLastError());
   fd_count_launch(1);
   return 0;

@@ -207,8 +207,20 @@ class GaussianDiffusion(nn.Module):
         s = getattr(self, "_seed_override", None)
         return (int(s) if s is not None else int(torch.initial_seed())) & (2 ** 63 - 1)
 
-    def _randn(self, shape, device):
-        out = torch.empty(shape, dtype=torch.float32, device=device)
+    def _sampler_ws(self, dev, B, T, M, E):
+        key = (str(dev), B, T, M, E)
+        ws = getattr(self, "_sws", None)
+        if ws is None or ws["key"] != key:
+            ws = {"key": key, "x": torch.empty((B, T, M), dtype=torch.float32, device=dev),
+                  "eps": torch.empty((B, T, M), dtype=torch.float32, device=dev),
+                  "x_planes": torch.empty((2, B, T, M), dtype=torch.int16, device=dev),
+                  "cond_planes": torch.empty((2, B, T, E), dtype=torch.int16, device=dev)}
+            self._sws = ws
+        return ws
+
+    def _randn(self, shape, device, out=None):
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=device)
         self._philox_calls += 1
         N.check(N.lib().fd_randn(N.ptr(out), out.numel(), self._rng_seed(), self._philox_calls << 20,
                                  getattr(self, "_subseq0", 0), N.stream_ptr(device)), "fd_randn")
@@ -317,9 +329,12 @@ class GaussianDiffusion(nn.Module):
         M = self.mel_bins
         self._subseq0 = int(first_item) * ((T * M + 3) // 4)      # first Philox subsequence (one per 4 elements)
         cmask = None if cond_masks is None else cond_masks.to(torch.uint8).contiguous()
-        cond_planes = N.split_nwc(features.to(torch.float32), prec, mask=cmask)       # once per call
+        # per-shape work buffers are kept between calls: stable pointers let the denoiser replay its captured CUDA
+        # graph from the first evaluation of every later call (one in-flight sampler call per module instance)
+        ws = self._sampler_ws(dev, B, T, M, E)
+        cond_planes = N.split_nwc(features.to(torch.float32), prec, mask=cmask, out=ws["cond_planes"])   # once per call
         if original_mel is None:
-            x = self._to_cl(x_T) if x_T is not None else self._randn((B, T, M), dev)
+            x = self._to_cl(x_T) if x_T is not None else self._randn((B, T, M), dev, out=ws["x"])
         else:
             # the reference passes original_mel as [B,M,T]-normalisable; it is normalised then used as x [B,M,T]
             om = original_mel.to(torch.float32)
@@ -329,14 +344,17 @@ class GaussianDiffusion(nn.Module):
             qn = self._to_cl(x_T) if (x_T is not None and original_mel is not None) else None
             x = self.q_sample(x_start=x, t=t0, noise=qn)
         x = x.contiguous()
-        x_planes = torch.empty((2, B, T, M), dtype=torch.int16, device=dev)
+        if x.data_ptr() != ws["x"].data_ptr():
+            ws["x"].copy_(x)
+            x = ws["x"]
+        x_planes = ws["x_planes"]
         N.split_nwc(x, prec, out=x_planes)
         chunks = torch.arange(0, self.num_timesteps - skip_steps, sampler_interval, dtype=torch.long).flip(0).tolist()
         it = chunks
         if progress and noise_predictor in ("naive", "plms"):
             from tqdm import tqdm
             it = tqdm(chunks)
-        eps = torch.empty((B, T, M), dtype=torch.float32, device=dev)
+        eps = ws["eps"]
         seed = self._rng_seed()
         # converted once per call: the denoiser replays a captured CUDA graph when it sees the same buffers again
         if x_masks is not None:

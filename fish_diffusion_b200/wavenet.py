@@ -370,9 +370,19 @@ class WaveNet(nn.Module):
             N.check(lib.fd_wavenet_fwd(ctypes.byref(d), st), "fd_wavenet_fwd")
             return out
         if ent["graph"] is None:
+            # capture on a side stream without torch.cuda.graph()'s device synchronise + empty_cache (the call sits in
+            # the middle of a sampler loop); nothing inside allocates
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                N.check(lib.fd_wavenet_fwd(ctypes.byref(d), N.stream_ptr(dev)), "fd_wavenet_fwd")
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    N.check(lib.fd_wavenet_fwd(ctypes.byref(d), N.stream_ptr(dev)), "fd_wavenet_fwd")
+                finally:
+                    g.capture_end()
+            cur.wait_stream(side)
             ent["graph"] = g
         ent["graph"].replay()
         return out

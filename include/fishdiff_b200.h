@@ -47,7 +47,7 @@ void fd_set_device(int device);
 long long fd_launch_count(void);
 /* per-launch device timing of the tap-GEMM kernels (CUDA events on the launching stream), used by bench.py for
  * the roofline entry: kind = epilogue*2 + (backend==SIMT); epilogue 0 linear, 1 gate (WaveNet GEMM1),
- * 2 res/skip (WaveNet GEMM2), 3 DFT magnitude.  fd_prof_collect synchronises the device, fills ms_sum[k]/count[k]
+ * 2 res/skip (WaveNet GEMM2), 3 DFT magnitude; kinds 8..11 = fused ResBlock pair kernel at C = 128/64/32/16.  fd_prof_collect synchronises the device, fills ms_sum[k]/count[k]
  * for k < nkinds, resets the log and returns 1 if the log overflowed (65536 launches), 0 otherwise, <0 on error. */
 void fd_prof_enable(int on);
 int fd_prof_collect(double* ms_sum, long long* count, int nkinds);
