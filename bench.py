@@ -634,6 +634,8 @@ def bench_train(torch, N, dev, rank, world, timed, pk, B=20, T=1000, steps=5, wa
         for _ in range(warmup):
             tr.step(feats, mel)
         ms = timed(lambda: tr.step(feats, mel), steps)
+        tr.step(feats, mel, timing=True)
+        tr.step(feats, mel, timing=True)        # fills last_split_ms with the split of the previous step
         ent = {"ms_per_step": ms, "samples_per_sec": world * B / (ms * 1e-3),
                "mel_frames_per_sec": world * B * T / (ms * 1e-3),
                "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
@@ -642,6 +644,13 @@ def bench_train(torch, N, dev, rank, world, timed, pk, B=20, T=1000, steps=5, wa
         if split:
             ent["split_ms"] = split
         if precision == "f16x1":
+            if world > 1:      # the same step without any gradient reduction: what the all-reduce costs on top
+                tr0 = DenoiserTrainer(diff, device=dev, sync="none")
+                tr0.step(feats, mel)
+                ent["ms_per_step_without_allreduce"] = timed(lambda: tr0.step(feats, mel), steps)
+                ent["allreduce_exposed_ms"] = ms - ent["ms_per_step_without_allreduce"]
+                diff.denoise_fn.grad_sync = None
+                del tr0
             with torch.no_grad():
                 diff.train_step(feats, mel)
                 ent["fwd_only_ms"] = timed(lambda: diff.train_step(feats, mel), steps)

@@ -82,6 +82,20 @@ class WaveNetFwdDesc(ctypes.Structure):
     ]
 
 
+class WaveNetBwdDesc(ctypes.Structure):
+    """struct fd_wavenet_bwd_desc (include/fishdiff_b200.h)."""
+    _fields_ = [
+        ("x_planes", c_void_p), ("y_planes", c_void_p), ("z_planes", c_void_p), ("cond_planes", c_void_p),
+        ("dx_next", c_void_p), ("dskip", c_void_p), ("w2t", c_void_p), ("w1t", c_void_p), ("wct", c_void_p),
+        ("w2t_inv", c_float), ("w1t_inv", c_float), ("wct_inv", c_float),
+        ("dx_out", c_void_p), ("dx_f32", c_void_p), ("d_cond", c_void_p), ("gw1", c_void_p), ("gw2", c_void_p),
+        ("cs_dy", c_void_p), ("cs_edge", c_void_p), ("cs_dx", c_void_p), ("dz", c_void_p), ("dy", c_void_p),
+        ("part1", c_void_p), ("part2", c_void_p), ("splits1", c_int), ("splits2", c_int),
+        ("B", c_int), ("T", c_int), ("C", c_int), ("E", c_int), ("dilation", c_int), ("gate_tile", c_int),
+        ("inv_S", c_float), ("prec", c_int), ("backend", c_int),
+    ]
+
+
 class WgradDesc(ctypes.Structure):
     """struct fd_wgrad_desc (include/fishdiff_b200.h)."""
     _fields_ = [
@@ -97,6 +111,7 @@ _SIGS = {
     "fd_gemm_cl_fwd": (c_int, [POINTER(GemmDesc), c_void_p]),
     "fd_wavenet_pack_layers": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fd_wgrad_cl": (c_int, [POINTER(WgradDesc), c_void_p]),
+    "fd_wavenet_block_bwd": (c_int, [POINTER(WaveNetBwdDesc), c_void_p]),
     "fd_colsum_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "fd_wavenet_block_fwd_train": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_void_p, c_float] +
                                    [c_int] * 6 + [c_float, c_float, c_int, c_int, c_int, c_void_p]),
@@ -379,6 +394,17 @@ def wgrad_supported(row_segs, col_segs) -> bool:
     """Shapes the direct (MN-major tcgen05) weight-gradient kernel takes: every segment a multiple of 64 channels."""
     return (1 <= len(row_segs) <= 2 and 1 <= len(col_segs) <= 8 and all(w % 64 == 0 and w > 0 for *_, w in row_segs)
             and all(w % 64 == 0 and w > 0 for *_, w in col_segs))
+
+
+def wgrad_splits(R, Cc, B, T):
+    """Item splits of a direct weight-gradient GEMM (see wgrad_cl): enough work units for ~2 waves of the 148 SMs, at
+    most one partial per item, and one TMEM accumulation run kept to <= ~2048 time steps."""
+    bn = 256 if Cc % 256 == 0 else 128 if Cc % 128 == 0 else 64
+    tiles = ((R + 127) // 128) * (Cc // bn)
+    splits = max(1, min(B, -(-296 // tiles)))
+    splits = max(splits, -(-B // max(1, 2048 // T)))
+    ips = -(-B // splits)
+    return -(-B // ips)
 
 
 def wgrad_cl(row_srcs, col_srcs, row_segs, col_segs, B, T, *, scale=1.0, prec=PREC_F16, splits=None, out=None):

@@ -2,6 +2,7 @@
 // are tap-GEMM launches (fd_tapgemm_*.cu): data gradients use transposed packed weights with mirrored tap shifts,
 // weight gradients use the same kernel with "rows" = output channels and K = time, fed by the folded transposes
 // produced here (wavenet.py:106-120 differentiated by hand; checked against the reference's autograd in the tests).
+#include <cstring>
 #include "fd_common.cuh"
 #include "fd_host.h"
 
@@ -230,6 +231,98 @@ int fd_reduce_batch(const float* in, float* out, int B, long long n, float scale
   k_reduce_batch<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(in, out, B, n, scale);
   FD_LAUNCHED();
   return 0;
+}
+
+int fd_wavenet_block_bwd(const fd_wavenet_bwd_desc* d, void* stream) {
+  FD_DEVICE_GUARD();
+  FD_REQUIRE(d != nullptr, "fd_wavenet_block_bwd: null descriptor");
+  const int B = d->B, T = d->T, C = d->C, E = d->E, dil = d->dilation;
+  FD_REQUIRE(B > 0 && T > 0 && C % 64 == 0 && E % 64 == 0 && dil > 0, "fd_wavenet_block_bwd: bad shape B=%d T=%d C=%d E=%d", B, T, C, E);
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  const long long rows = (long long)B * T;
+  int rc;
+  // ---- dz = [dx_next | d_skip] . W2 (K offset C selects the skip half when there is no residual gradient)
+  {
+    fd_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.w = d->w2t; g.n_total = C; g.k_total = 2 * C; g.B = B; g.T = T;
+    g.w_inv_scale = d->w2t_inv; g.res_scale = 1.f; g.post_scale = 1.f; g.planes_scale = 1.f;
+    g.out_f32 = d->dz; g.prec = d->prec; g.backend = d->backend;
+    if (d->dx_next == nullptr) {
+      g.src[0] = d->dskip; g.src_C[0] = C; g.num_seg = 1; g.w_kshift = C;
+      g.seg_src[0] = 0; g.seg_shift[0] = 0; g.seg_coff[0] = 0; g.seg_klen[0] = C;
+    } else {
+      g.src[0] = d->dx_next; g.src_C[0] = C; g.src[1] = d->dskip; g.src_C[1] = C; g.num_seg = 2;
+      g.seg_src[0] = 0; g.seg_klen[0] = C; g.seg_src[1] = 1; g.seg_klen[1] = C;
+    }
+    rc = fd_gemm_cl_fwd(&g, stream);
+    if (rc) return rc;
+  }
+  rc = fd_gate_bwd(d->dz, d->y_planes, d->dy, rows, C, d->gate_tile, d->prec & 0xF, stream);
+  if (rc) return rc;
+  // ---- gw2 = [dx_next ; d_skip]^T . z
+  {
+    fd_wgrad_desc w;
+    memset(&w, 0, sizeof(w));
+    w.col_src[0] = d->z_planes; w.col_C[0] = C; w.num_col_seg = 1; w.col_seg_width[0] = C;
+    w.B = B; w.T = T; w.splits = d->splits2; w.part = d->part2; w.acc_scale = 1.f; w.prec = d->prec;
+    float* out = d->gw2;
+    int R = 2 * C;
+    if (d->dx_next == nullptr) {
+      FD_CHECK_CUDA(cudaMemsetAsync(d->gw2, 0, (size_t)C * C * sizeof(float), (cudaStream_t)stream));
+      w.row_src[0] = d->dskip; w.row_C[0] = C; w.num_row_seg = 1; w.row_seg_width[0] = C;
+      out = d->gw2 + (size_t)C * C; R = C;
+    } else {
+      w.row_src[0] = d->dx_next; w.row_C[0] = C; w.row_src[1] = d->dskip; w.row_C[1] = C; w.num_row_seg = 2;
+      w.row_seg_src[0] = 0; w.row_seg_width[0] = C; w.row_seg_src[1] = 1; w.row_seg_width[1] = C;
+    }
+    rc = fd_wgrad_cl(&w, stream);
+    if (rc) return rc;
+    rc = fd_reduce_batch(d->part2, out, d->splits2, (long long)R * C, d->inv_S, stream);
+    if (rc) return rc;
+  }
+  // ---- gw1 = dy^T . [x(t-d) | x(t) | x(t+d) | cond]
+  {
+    fd_wgrad_desc w;
+    memset(&w, 0, sizeof(w));
+    w.row_src[0] = d->dy; w.row_C[0] = 2 * C; w.num_row_seg = 1; w.row_seg_width[0] = 2 * C;
+    w.col_src[0] = d->x_planes; w.col_C[0] = C; w.col_src[1] = d->cond_planes; w.col_C[1] = E; w.num_col_seg = 4;
+    const int sh[3] = {-dil, 0, dil};
+    for (int j = 0; j < 3; ++j) { w.col_seg_src[j] = 0; w.col_seg_shift[j] = sh[j]; w.col_seg_width[j] = C; }
+    w.col_seg_src[3] = 1; w.col_seg_width[3] = E;
+    w.B = B; w.T = T; w.splits = d->splits1; w.part = d->part1; w.acc_scale = 1.f; w.prec = d->prec;
+    rc = fd_wgrad_cl(&w, stream);
+    if (rc) return rc;
+    rc = fd_reduce_batch(d->part1, d->gw1, d->splits1, (long long)2 * C * (3 * C + E), d->inv_S, stream);
+    if (rc) return rc;
+  }
+  rc = fd_colsum(d->dy, nullptr, d->cs_dy, B, T, 2 * C, d->inv_S, d->prec & 0xF, stream);
+  if (rc) return rc;
+  rc = fd_colsum_edges(d->dy, d->cs_edge, B, T, 2 * C, dil < T ? dil : T, d->inv_S, d->prec & 0xF, stream);
+  if (rc) return rc;
+  // ---- dx_l = conv^T(dy) + dx_next/sqrt2 (mirrored tap shifts, K = 6C)
+  {
+    fd_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.src[0] = d->dy; g.src_C[0] = 2 * C; g.w = d->w1t; g.n_total = C; g.k_total = 6 * C; g.B = B; g.T = T; g.num_seg = 3;
+    const int sh[3] = {dil, 0, -dil};
+    for (int j = 0; j < 3; ++j) { g.seg_src[j] = 0; g.seg_shift[j] = sh[j]; g.seg_klen[j] = 2 * C; }
+    g.res_planes = d->dx_next; g.res_scale = inv_sqrt2; g.w_inv_scale = d->w1t_inv; g.post_scale = 1.f; g.planes_scale = 1.f;
+    g.out_planes = d->dx_out; g.out_f32 = d->dx_f32; g.prec = d->prec; g.backend = d->backend;
+    rc = fd_gemm_cl_fwd(&g, stream);
+    if (rc) return rc;
+  }
+  if (d->d_cond != nullptr) {
+    fd_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.src[0] = d->dy; g.src_C[0] = 2 * C; g.w = d->wct; g.n_total = E; g.k_total = 2 * C; g.B = B; g.T = T; g.num_seg = 1;
+    g.seg_klen[0] = 2 * C;
+    g.w_inv_scale = d->wct_inv * d->inv_S; g.res_scale = 1.f; g.post_scale = 1.f; g.planes_scale = 1.f;
+    g.out_f32 = d->d_cond; g.out_accum = 1; g.prec = d->prec; g.backend = d->backend;
+    rc = fd_gemm_cl_fwd(&g, stream);
+    if (rc) return rc;
+  }
+  return fd_colsum(d->dx_out, nullptr, d->cs_dx, B, T, C, d->inv_S, d->prec & 0xF, stream);
 }
 
 }  // extern "C"

@@ -39,6 +39,18 @@ def _bwd_packs(net, pk, device):
     return pk["_bwd"]
 
 
+def _add_step_vector_term(gw1, cs_dy, cs_edge, dl, Bs, C):
+    """gw1 [n,2C,KT] += rank-one term of the conv input x + d_l (zero padded): sum_t dy[t,r] * d[c] over the steps where
+    tap j reads inside [0,T) = (column sums of dy minus their first / last `dil` edge sums) (x) d_l."""
+    n = gw1.shape[0]
+    wj = torch.stack([cs_dy - cs_edge[:, 0], cs_dy, cs_dy - cs_edge[:, 1]], dim=1)        # [n,3,B,2C]
+    if Bs > 1:
+        corr = torch.einsum("ljbr,lbc->lrjc", wj, dl)
+    else:
+        corr = torch.einsum("ljr,lc->lrjc", wj.sum(2), dl[:, 0])
+    gw1[:, :, :3 * C] += corr.reshape(n, 2 * C, 3 * C)
+
+
 class WaveNetTrainFn(torch.autograd.Function):
     """eps_cl = f(x_cl [B,T,M], cond_cl [B,T,E], d [Bs,L,C], *conv weights);  see WaveNet.train_param_list().
     `masks` = (x_mask, cond_mask) uint8 [B,T] or None each, the reference's masked_fill points (wavenet.py:217-221,
@@ -224,7 +236,50 @@ class WaveNetTrainFn(torch.autograd.Function):
         dx_bufs = [torch.empty((2, B, T, C), **i16) for _ in range(2)]
         gw1_all = torch.empty((L, 2 * C, KT), **f32)       # packed row order, un-permuted once at the end
         gb1_all = torch.empty((L, 2 * C), **f32)
-        for l in reversed(range(L)):
+        sync = getattr(net, "grad_sync", None) if direct else None     # overlapped gradient all-reduce (train.GradSync)
+        net._synced_in_backward = sync is not None
+        if direct:
+            # ---- one native call per block (fd_wavenet_block_bwd); per-layer column sums land in [L, ...] arrays and are
+            #      turned into bias / step-vector gradients for all layers at once after the loop
+            cs_x = torch.zeros((L + 1, B, C), **f32)                              # colsum of d(x_l); row L stays zero
+            splits1, splits2 = N.wgrad_splits(2 * C, KT, B, T), N.wgrad_splits(2 * C, C, B, T)
+            part1 = torch.empty((splits1, 2 * C, KT), **f32)
+            part2 = torch.empty((splits2, 2 * C, C), **f32)
+            bd = N.WaveNetBwdDesc()
+            bd.cond_planes, bd.dskip = N.ptr(sv["cond_planes"]), N.ptr(dskip_planes)
+            bd.d_cond, bd.dz, bd.dy = N.ptr(d_cond), N.ptr(dz), N.ptr(dy)
+            bd.part1, bd.part2, bd.splits1, bd.splits2 = N.ptr(part1), N.ptr(part2), splits1, splits2
+            bd.B, bd.T, bd.C, bd.E, bd.gate_tile = B, T, C, E, gate_tile
+            bd.inv_S, bd.prec, bd.backend = inv_S, mma, N.BACKEND_TC
+            dl_all = sv["d"].transpose(0, 1)                                       # [L,Bs,C]
+            bucket = sync.bucket_layers if sync is not None else L
+            import ctypes as _ct
+            for l in reversed(range(L)):
+                dx_l = dx_bufs[l & 1]
+                bd.x_planes, bd.y_planes, bd.z_planes = N.ptr(sv["xs"][l]), N.ptr(sv["ys"][l]), N.ptr(sv["zs"][l])
+                bd.dx_next = N.ptr(dx_next)
+                bd.w2t, bd.w1t, bd.wct = N.ptr(bw["w2t"][l]), N.ptr(bw["w1t"][l]), N.ptr(bw["wct"][l])
+                bd.w2t_inv, bd.w1t_inv, bd.wct_inv = bw["w2t_inv"][l], bw["w1t_inv"][l], bw["wct_inv"][l]
+                bd.dx_out, bd.dx_f32 = N.ptr(dx_l), N.ptr(dx0 if l == 0 else None)
+                bd.gw1, bd.gw2 = N.ptr(gw1_all[l]), N.ptr(gw2_all[l])
+                bd.cs_dy, bd.cs_edge, bd.cs_dx = N.ptr(cs_dy[l]), N.ptr(cs_edge[l]), N.ptr(cs_x[l])
+                bd.dilation = pk["dil"][l]
+                N.check(lib.fd_wavenet_block_bwd(_ct.byref(bd), st), "fd_wavenet_block_bwd")
+                dx_next = dx_l
+                if sync is not None and (l % bucket == 0):
+                    # layers [l, hi) are final: add their rank-one step-vector term (it depends on this rank's d) and
+                    # start the all-reduce of the bucket; it overlaps the backward of the layers below
+                    hi = min(L, l + bucket)
+                    _add_step_vector_term(gw1_all[l:hi], cs_dy[l:hi], cs_edge[l:hi], dl_all[l:hi], Bs, C)
+                    sync.reduce_async(gw1_all[l:hi], gw2_all[l:hi])
+            cs_next = None
+            d_d = cs_x[:L] - cs_x[1:] * inv_sqrt2                                  # [L,B,C] gradient wrt the step vectors d_l
+            d_d = d_d.transpose(0, 1) if Bs > 1 else d_d.sum(1, keepdim=True).transpose(0, 1)
+            d_d = d_d.contiguous()
+            gb2_all = torch.cat([cs_x[1:].sum(1) * inv_sqrt2, cs_skip.sum(0).expand(L, C)], dim=1)   # [L,2C]
+            for l in range(L):
+                grads[f"l{l}.b2"] = gb2_all[l]
+        for l in (reversed(range(L)) if not direct else ()):
             dil = pk["dil"][l]
             if dx_next is None:     # K offset C selects the skip half of W2^T (aligned: C % 8 == 0)
                 N.gemm_cl(dskip_planes, C, bw["w2t"][l], C, 2 * C, B, T, [(0, 0, 0, C)], w_kshift=C, out_f32=dz,
@@ -282,13 +337,10 @@ class WaveNetTrainFn(torch.autograd.Function):
         if direct:
             gb1_all = cs_dy.sum(1)
             # conv input is x + d_l (zero padded): sum_t dy[t,r] * d[c] over the steps where tap j reads inside [0,T)
-            wj = torch.stack([cs_dy - cs_edge[:, 0], cs_dy, cs_dy - cs_edge[:, 1]], dim=1)        # [L,3,B,2C]
-            dl = sv["d"].transpose(0, 1)                                                            # [L,Bs,C]
-            if Bs > 1:
-                corr = torch.einsum("ljbr,lbc->lrjc", wj, dl)
+            if sync is None:
+                _add_step_vector_term(gw1_all, cs_dy, cs_edge, sv["d"].transpose(0, 1), Bs, C)
             else:
-                corr = torch.einsum("ljr,lc->lrjc", wj.sum(2), dl[:, 0])
-            gw1_all[:, :, :3 * C] += corr.reshape(L, 2 * C, 3 * C)
+                sync.wait()            # every bucket reduced before the gradients are laid out for autograd
             gw2_all[:, :C] *= inv_sqrt2
             for l in range(L):
                 grads[f"l{l}.w2"] = gw2_all[l]

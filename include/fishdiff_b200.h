@@ -344,6 +344,41 @@ int fd_wgrad_cl(const fd_wgrad_desc* d, void* stream);
 /* out[i] = scale * sum_b in[b][i]  (reduction of the per-item weight-gradient partials) */
 int fd_reduce_batch(const float* in, float* out, int B, long long n, float scale, void* stream);
 
+/* Backward of ONE ResidualBlock (autograd of modules/wavenet.py:106-120) as one native call: the 5 GEMM launches and the
+ * elementwise / reduction kernels around them, issued back to back on `stream`:
+ *   dz   = [dx_next/sqrt2 | d_skip] . W2            (fd_gemm_cl_fwd, two sources; skip half only above the last layer)
+ *   dy   = gate backward of dz on the saved pre-activations (fd_gate_bwd)
+ *   gw2  = [dx_next ; d_skip]^T . z                  (fd_wgrad_cl + fd_reduce_batch; the 1/sqrt2 of the residual rows is
+ *                                                     applied by the caller to all layers at once)
+ *   gw1  = dy^T . [x(t-d) | x(t) | x(t+d) | cond]   (one weight-gradient GEMM, packed row order)
+ *   cs_dy / cs_edge = column sums of dy (bias gradient, rank-one step-vector term of gw1)
+ *   dx   = conv^T(dy) + dx_next/sqrt2 -> planes (+ fp32 copy when dx_f32 != NULL);  d_cond += dy . Wc;  cs_dx = colsum(dx)
+ * All gradients inside the chain carry the caller's power-of-two scale S; results that leave it are multiplied by
+ * inv_S.  cs_dy [B][2C], cs_edge [2][B][2C], cs_dx [B][C] must be zero on entry.  part1 / part2: fp32 workspaces of
+ * splits1*2C*(3C+E) and splits2*2C*C floats.  Needs C, E multiples of 64 (the direct weight-gradient kernel). */
+typedef struct fd_wavenet_bwd_desc {
+  const uint16_t* x_planes;    /* xs[l]   [2][B][T][C]  residual stream entering the layer */
+  const uint16_t* y_planes;    /* ys[l]   [2][B][T][2C] gate/filter pre-activations, packed order */
+  const uint16_t* z_planes;    /* zs[l]   [2][B][T][C]  gated activations */
+  const uint16_t* cond_planes; /* [2][B][T][E] */
+  const uint16_t* dx_next;     /* planes of d(x_{l+1}) or NULL above the last layer */
+  const uint16_t* dskip;       /* planes of d(skip_l) (the same for every layer) */
+  const uint16_t* w2t; const uint16_t* w1t; const uint16_t* wct;   /* transposed packs [2][C][2C], [2][C][6C], [2][E][2C] */
+  float w2t_inv, w1t_inv, wct_inv;
+  uint16_t* dx_out;            /* planes of d(x_l) */
+  float* dx_f32;               /* fp32 copy of d(x_l) or NULL */
+  float* d_cond;               /* fp32 [B][T][E], accumulated, or NULL */
+  float* gw1; float* gw2;      /* [2C][3C+E], [2C][C] */
+  float* cs_dy; float* cs_edge; float* cs_dx;
+  float* dz; uint16_t* dy;     /* workspaces [B][T][C] fp32, [2][B][T][2C] planes */
+  float* part1; float* part2;
+  int splits1, splits2;
+  int B, T, C, E, dilation, gate_tile;
+  float inv_S;
+  int prec, backend;
+} fd_wavenet_bwd_desc;
+int fd_wavenet_block_bwd(const fd_wavenet_bwd_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

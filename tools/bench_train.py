@@ -40,7 +40,9 @@ def main():
     ap.add_argument("--check-ddp", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced network (tests)")
     ap.add_argument("--precision", default="f16", help="f16 | bf16 (three split products) or f16x1 | bf16x1 (one product)")
-    ap.add_argument("--fp16-hook", action="store_true", help="use the reference's fp16_compress_hook")
+    ap.add_argument("--fp16-hook", action="store_true", help="use the reference's fp16_compress_hook (sync=torch)")
+    ap.add_argument("--sync", default="bucketed", choices=["bucketed", "torch", "none"],
+                    help="gradient reduction: overlapped buckets from inside the native backward / stock DDP / none")
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -64,9 +66,12 @@ def main():
 
     if args.check_ddp:
         diff = build(dev, cfg)
-        tr = DenoiserTrainer(diff, fp16_compress=False, device=dev)
+        tr = DenoiserTrainer(diff, fp16_compress=False, device=dev, sync=args.sync, clip=0)
         model = tr.ddp if tr.ddp is not None else tr.module
         model(feats, mel, t=t, noise=noise).backward()
+        if tr.sync is not None:
+            tr.sync.wait()
+            tr._reduce_rest()
         ref = build(dev, cfg)
         DenoiserTrainer(ref).module(feats_all.to(dev), mel_all.to(dev), t=t_all.to(dev), noise=noise_all.to(dev)).backward()
         worst = 0.0
@@ -82,7 +87,7 @@ def main():
         sys.exit(0 if worst < 1e-3 else 1)
 
     diff = build(dev, cfg)
-    tr = DenoiserTrainer(diff, device=dev, fp16_compress=args.fp16_hook)
+    tr = DenoiserTrainer(diff, device=dev, fp16_compress=args.fp16_hook, sync=args.sync)
     for _ in range(args.warmup):
         tr.step(feats, mel)
     torch.cuda.synchronize()
@@ -114,7 +119,7 @@ def main():
             "fwd_only_ms": fwd_ms, "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
             "gpu_launches_per_step": (N.launch_count() - l0) // (2 * args.steps) if False else None,
             "loss": float(loss), "optimizer": "AdamW(8e-4, wd 1e-2, betas (0.9,0.98), eps 1e-9), clip 0.5",
-            "ddp": ("torch DDP over NCCL, static_graph" + (", fp16_compress_hook" if args.fp16_hook else "")) if world > 1 else "single process",
+            "ddp": (args.sync + (", fp16_compress_hook" if args.fp16_hook else "")) if world > 1 else "single process",
             "dtype": ("%s operands, fp32 accumulate (single tcgen05 product)" % args.precision[:-2]) if args.precision.endswith("x1") else "f32 (3x %s split-product tcgen05)" % args.precision, "precision": args.precision, "data": "synthetic"}))
     if world > 1:
         torch.distributed.destroy_process_group()
