@@ -649,7 +649,6 @@ def bench_train(torch, N, dev, rank, world, timed, pk, B=20, T=1000, steps=5, wa
                 tr0.step(feats, mel)
                 ent["ms_per_step_without_allreduce"] = timed(lambda: tr0.step(feats, mel), steps)
                 ent["allreduce_exposed_ms"] = ms - ent["ms_per_step_without_allreduce"]
-                diff.denoise_fn.grad_sync = None
                 del tr0
             with torch.no_grad():
                 diff.train_step(feats, mel)

@@ -10,7 +10,8 @@ from .registry import DENOISERS, DIFFUSIONS, VOCODERS, Registry  # noqa: F401
 from .wavenet import WaveNet  # noqa: F401
 from .diffusion import GaussianDiffusion, NaiveNoisePredictor, PLMSNoisePredictor, UNIPCNoisePredictor  # noqa: F401
 from .nsf_hifigan import Generator, NsfHifiGAN  # noqa: F401
-from .mel import PitchAdjustableMelSpectrogram, dynamic_range_compression  # noqa: F401
+from .mel import (MelSpectrogram, PitchAdjustableMelSpectrogram, dynamic_range_compression, get_mel_from_audio,  # noqa: F401
+                  get_mel_transform)
 from .diffsinger import ENCODERS, DiffSinger, NaiveProjectionEncoder, load_checkpoint, pitch_to_scale  # noqa: F401
 from .fastspeech import FastSpeech2Encoder  # noqa: F401
 from .pipeline import BatchedSynthesizer, plan_batches  # noqa: F401

@@ -279,8 +279,8 @@ int fd_conv_cl_fwd(const fd_conv_desc* d, void* stream) {
   return run(p, d->backend, (cudaStream_t)stream);
 }
 
-int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
-                    int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, int prec,
+int fd_stft_mag_eps_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
+                    int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, float mag_eps, int prec,
                     int backend, void* stream) {
   FD_DEVICE_GUARD();
   FD_REQUIRE(n_fft % 64 == 0 && hop % 8 == 0 && NB % 128 == 0, "fd_stft_mag_fwd: n_fft=%d hop=%d NB=%d unsupported",
@@ -295,9 +295,16 @@ int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag
   p.src[0] = padded; p.src_C[0] = n_fft;
   p.src_rs[0] = hop; p.src_bs[0] = pitch; p.src_ps[0] = (long long)B * pitch;
   p.w = dft_w; p.acc_scale = w_inv_scale;
-  p.epi = FD_EPI_MAG; p.gate_tile = 256; p.C = NB; p.mag_scale = mag_scale;
+  p.epi = FD_EPI_MAG; p.gate_tile = 256; p.C = NB; p.mag_scale = mag_scale; p.mag_eps = mag_eps;
   p.out_planes = mag_planes;
   return run(p, backend, (cudaStream_t)stream);
+}
+
+int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
+                    int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, int prec,
+                    int backend, void* stream) {
+  return fd_stft_mag_eps_fwd(padded, dft_w, mag_planes, B, Np, n_fft, hop, frames, NB, w_inv_scale, mag_scale, 1e-9f, prec,
+                             backend, stream);
 }
 
 int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream) {

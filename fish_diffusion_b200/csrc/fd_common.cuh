@@ -91,8 +91,9 @@ struct FdTapGemm {
   int gate_tile;            // NT (column tile the weights were packed for)
 
   // ---- FD_EPI_MAG (framed DFT): same column pairing as the gate epilogue (re | im per tile);
-  //      out_planes[b,t,c] = split(sqrt(re^2 + im^2 + 1e-9) * mag_scale), channel count = C
+  //      out_planes[b,t,c] = split(sqrt(re^2 + im^2 + mag_eps) * mag_scale), channel count = C
   float mag_scale;
+  float mag_eps;            // 1e-9 (pitch_adjustable_mel.py:85) or 0 (torchaudio Spectrogram(power=1), utils/audio.py:45)
 
   // ---- FD_EPI_RES_SKIP (WaveNet GEMM2): columns [0,C) residual, [C,2C) skip.
   //      x' = (x + y_res) / sqrt(2)  -> x planes updated in place
@@ -365,7 +366,7 @@ __device__ __forceinline__ void fd_epi_mag(const FdTapGemm& p, int b, int t, int
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const float r = re[i] * p.acc_scale, q = im[i] * p.acc_scale;
-    z[i] = sqrtf(r * r + q * q + 1e-9f) * p.mag_scale;
+    z[i] = sqrtf(r * r + q * q + p.mag_eps) * p.mag_scale;
   }
   const size_t plane_elems = (size_t)p.B * p.T * p.C;
   const size_t off = ((size_t)b * p.T + t) * p.C + zc0;

@@ -124,39 +124,53 @@ class PitchAdjustableMelSpectrogram:
     @torch.no_grad()
     def __call__(self, y, key_shift=0, speed=1.0):
         """y [B,N] float -> [B, n_mels, frames] (linear mel magnitudes), pitch_adjustable_mel.py:33-96."""
-        N.require_cuda(y, "y")
-        dev = y.device
-        prec = N.prec_code(self.precision)
         factor = 2 ** (key_shift / 12)
         n_fft_new = int(np.round(self.n_fft * factor))
         win_new = int(np.round(self.win_size * factor))
         hop = int(np.round(self.hop_length * speed))
-        if hop % 8 != 0:
-            raise ValueError(f"hop_length*speed = {hop} must be a multiple of 8 samples for the framed TMA view")
+        pad = int((win_new - hop) / 2)
+        mag_scale = 1.0 if key_shift == 0 else float(self.win_size) / float(win_new)
+        return self._stft_mel(y, n_fft_new, win_new, hop, pad, mag_scale, 1e-9)
+
+    def _stft_mel(self, y, n_fft_new, win_new, hop, pad, mag_scale, mag_eps):
+        """reflect pad by `pad` -> framed DFT magnitude (window folded into the DFT matrix) -> mel filterbank."""
+        N.require_cuda(y, "y")
+        dev = y.device
+        prec = N.prec_code(self.precision)
         y = y.to(torch.float32).contiguous()
         B, n = y.shape
-        pad = int((win_new - hop) / 2)
         w_planes, w_inv, kpad, bins = self._dft_weights(n_fft_new, win_new, dev, prec)
         Np = n + 2 * pad
         frames = 1 + (Np - n_fft_new) // hop
-        # room for the zero-weighted K padding of the last frame
-        need = (frames - 1) * hop + kpad
-        pitch = (max(Np, need) + 7) // 8 * 8
         st = N.stream_ptr(dev)
         lib = N.lib()
-        padded = torch.zeros((2, B, pitch), dtype=torch.int16, device=dev)
-        if pitch == (Np + 7) // 8 * 8:
-            N.check(lib.fd_reflect_pad_split(N.ptr(y), N.ptr(padded), B, n, pad, prec, st), "fd_reflect_pad_split")
-            np_arg = Np
+        if hop % 8 == 0:
+            # frames are overlapping rows of the padded signal: a TMA view with row stride = hop (16-byte aligned)
+            need = (frames - 1) * hop + kpad          # room for the zero-weighted K padding of the last frame
+            pitch = (max(Np, need) + 7) // 8 * 8
+            padded = torch.zeros((2, B, pitch), dtype=torch.int16, device=dev)
+            if pitch == (Np + 7) // 8 * 8:
+                N.check(lib.fd_reflect_pad_split(N.ptr(y), N.ptr(padded), B, n, pad, prec, st), "fd_reflect_pad_split")
+                np_arg = Np
+            else:
+                tmp = torch.zeros((2, B, (Np + 7) // 8 * 8), dtype=torch.int16, device=dev)
+                N.check(lib.fd_reflect_pad_split(N.ptr(y), N.ptr(tmp), B, n, pad, prec, st), "fd_reflect_pad_split")
+                padded[:, :, :tmp.shape[2]] = tmp
+                np_arg = pitch
+            row_stride = hop
         else:
-            tmp = torch.zeros((2, B, (Np + 7) // 8 * 8), dtype=torch.int16, device=dev)
-            N.check(lib.fd_reflect_pad_split(N.ptr(y), N.ptr(tmp), B, n, pad, prec, st), "fd_reflect_pad_split")
-            padded[:, :, :tmp.shape[2]] = tmp
-            np_arg = pitch
+            # arbitrary hop (time-stretch augmentation draws e.g. 512*1.1 = 563): the frames are gathered once into an
+            # aligned [frames, kpad] buffer and read as non-overlapping rows
+            yp = torch.nn.functional.pad(y[:, None], (pad, pad), mode="reflect")[:, 0] if pad > 0 else y
+            fr = yp.unfold(-1, n_fft_new, hop)[:, :frames]                         # [B, frames, n_fft_new] view
+            buf = torch.zeros((B, frames, kpad), dtype=torch.float32, device=dev)
+            buf[:, :, :n_fft_new] = fr
+            padded = N.split_nwc(buf, prec).reshape(2, B, frames * kpad)
+            np_arg, row_stride = frames * kpad, kpad
         mag = torch.empty((2, B, frames, self.NB), dtype=torch.int16, device=dev)
-        mag_scale = 1.0 if key_shift == 0 else float(self.win_size) / float(win_new)
-        N.check(lib.fd_stft_mag_fwd(N.ptr(padded), N.ptr(w_planes), N.ptr(mag), B, np_arg, kpad, hop, frames, self.NB,
-                                    w_inv, mag_scale, N.mma_code(self.precision), self._backend(), st), "fd_stft_mag_fwd")
+        N.check(lib.fd_stft_mag_eps_fwd(N.ptr(padded), N.ptr(w_planes), N.ptr(mag), B, np_arg, kpad, row_stride, frames,
+                                        self.NB, w_inv, mag_scale, mag_eps, N.mma_code(self.precision), self._backend(), st),
+                "fd_stft_mag_eps_fwd")
         mw, mw_inv = self._mel_weights(bins, dev, prec)
         mel_cl = torch.empty((B, frames, self.n_mels), dtype=torch.float32, device=dev)
         N.conv_cl(mag, mw, B, frames, self.NB, self.n_mels, [0], out_f32=mel_cl, w_inv_scale=mw_inv, prec=N.mma_code(self.precision),
@@ -165,3 +179,46 @@ class PitchAdjustableMelSpectrogram:
         N.check(lib.fd_transpose_nwc_to_ncw(N.ptr(mel_cl), N.ptr(out), B, frames, self.n_mels, st),
                 "fd_transpose_nwc_to_ncw")
         return out
+
+
+class MelSpectrogram(PitchAdjustableMelSpectrogram):
+    """What ``get_mel_transform`` returns: the torchaudio ``MelSpectrogram(power=1, center=True, pad_mode="reflect",
+    norm="slaney", mel_scale="slaney")`` of the reference's training / validation losses (utils/audio.py:31-60) on the
+    same framed-DFT + filterbank kernels.  Callable on [..., n] audio -> [..., n_mels, 1 + n // hop]."""
+
+    def __init__(self, sample_rate=44100, n_fft=2048, win_length=2048, hop_length=512, f_min=40, f_max=16000, n_mels=128,
+                 center=True, power=1.0, pad_mode="reflect", norm="slaney", mel_scale="slaney", precision="f16",
+                 backend="auto"):
+        if power != 1.0 or pad_mode != "reflect" or norm != "slaney" or mel_scale != "slaney" or not center:
+            raise NotImplementedError("MelSpectrogram: only the reference's configuration (power=1, center=True, "
+                                      "reflect padding, slaney norm / scale) is implemented")
+        super().__init__(sample_rate, n_fft, win_length, hop_length, f_min, f_max, n_mels, center=True,
+                         precision=precision, backend=backend)
+
+    def to(self, *args, **kwargs):          # the reference moves the torchaudio module to the audio's device
+        return self
+
+    @torch.no_grad()
+    def __call__(self, audio):
+        lead = audio.shape[:-1]
+        y = audio.reshape(-1, audio.shape[-1])
+        out = self._stft_mel(y, self.n_fft, self.win_size, self.hop_length, self.n_fft // 2, 1.0, 0.0)
+        return out.reshape(*lead, self.n_mels, out.shape[-1])
+
+
+def get_mel_transform(sample_rate=44100, n_fft=2048, win_length=2048, hop_length=512, f_min=40, f_max=16000, n_mels=128,
+                      center=True, power=1.0, pad_mode="reflect", norm="slaney", mel_scale="slaney", **kw):
+    """utils/audio.py:31-60."""
+    return MelSpectrogram(sample_rate, n_fft, win_length, hop_length, f_min, f_max, n_mels, center, power, pad_mode, norm,
+                          mel_scale, **kw)
+
+
+@torch.no_grad()
+def get_mel_from_audio(audio, sample_rate=44100, n_fft=2048, win_length=2048, hop_length=512, f_min=40, f_max=16000,
+                       n_mels=128, center=True, power=1.0, pad_mode="reflect", norm="slaney", mel_scale="slaney", **kw):
+    """utils/audio.py:63-109: audio [1, n] -> log-mel [n_mels, frames]."""
+    assert audio.ndim == 2, "Audio tensor must be 2D (1, n_samples)"
+    assert audio.shape[0] == 1, "Audio tensor must be mono"
+    tf = get_mel_transform(sample_rate, n_fft, win_length, hop_length, f_min, f_max, n_mels, center, power, pad_mode, norm,
+                           mel_scale, **kw)
+    return dynamic_range_compression(tf(audio))[0]

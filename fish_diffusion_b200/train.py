@@ -86,7 +86,8 @@ class DenoiserTrainer:
                 for p in diffusion.parameters():          # same starting point on every rank (what DDP's constructor does)
                     torch.distributed.broadcast(p.data, src=0)
                 self.sync = GradSync(bucket_layers=bucket_layers)
-                diffusion.denoise_fn.grad_sync = self.sync
+        if hasattr(diffusion, "denoise_fn"):
+            diffusion.denoise_fn.grad_sync = self.sync       # None: the backward reduces nothing itself
         params = list(diffusion.parameters())
         # same update rule as the reference's torch.optim.AdamW; the fused (single multi-tensor kernel) implementation
         fused = all(p.is_cuda for p in params)

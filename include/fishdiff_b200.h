@@ -248,6 +248,11 @@ int fd_reflect_pad_split(const float* wav, uint16_t* planes, int B, long long N,
 int fd_stft_mag_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
                     int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, int prec,
                     int backend, void* stream);
+/* same with an explicit epsilon inside the square root: 0 for torchaudio's Spectrogram(power=1) used by
+ * utils/audio.py:31-109 (get_mel_transform / get_mel_from_audio), 1e-9 for pitch_adjustable_mel.py:85 */
+int fd_stft_mag_eps_fwd(const uint16_t* padded, const uint16_t* dft_w, uint16_t* mag_planes, int B, long long Np,
+                    int n_fft, int hop, int frames, int NB, float w_inv_scale, float mag_scale, float mag_eps, int prec,
+                    int backend, void* stream);
 /* log(clamp(x, clip)) * out_scale over fp32 (audio.py:11-18 dynamic_range_compression) */
 int fd_log_clamp(const float* x, float* y, long long n, float clip, float out_scale, void* stream);
 

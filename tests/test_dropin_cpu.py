@@ -175,3 +175,58 @@ def test_transposed_conv_polyphase_packing_matches_definition():
                     if 0 <= kk < k and 0 <= q + dl < T:
                         got[:, q * u + r] += w[:, :, kk].T @ x[0, :, q + dl]
         assert np.allclose(got, want, atol=1e-12), (u, k)
+
+
+def test_cosine_schedule_product_buffers_bit_exact(golden, golden_cfg):
+    """noise_schedule="cosine" (diffusion.py:24-29: s=0.008, clip 0.999; the golden generator used max_beta=0.02, which the
+    cosine branch ignores): every product buffer equals the reference's, bit for bit."""
+    cfg = golden_cfg["WN_SMALL"]
+    diff = DIFFUSIONS.build(dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **cfg), mel_channels=16,
+                                 noise_schedule="cosine", max_beta=0.02, s=0.008, spec_min=[-5.0], spec_max=[0.0]))
+    g = golden("schedules")
+    for k, v in diff.naive_noise_predictor.state_dict().items():
+        assert np.array_equal(v.numpy().view(np.uint32), g[f"sched_cosine_naive_{k}"].view(np.uint32)), k
+    assert np.array_equal(diff.plms_noise_predictor.alphas_cumprod.numpy().view(np.uint32),
+                          g["sched_cosine_plms_alphas_cumprod"].view(np.uint32))
+    ns = diff.unipc_noise_predictor.noise_schedule
+    assert np.array_equal(ns.t_array.view(np.uint32), g["sched_cosine_unipc_t_array"].reshape(-1).view(np.uint32))
+    assert np.array_equal(ns.log_alpha_array.view(np.uint32),
+                          g["sched_cosine_unipc_log_alpha_array"].reshape(-1).view(np.uint32))
+    for name in ("betas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"):
+        assert getattr(diff, name).dtype == torch.float32 and getattr(diff, name).shape == (1000,)
+
+
+def test_reference_written_checkpoint_loads_strictly(golden_cfg):
+    """A checkpoint written by the reference classes (tests/golden/ref_ckpt_small.ckpt: Lightning layout, `model.` and
+    `ema_model.` prefixes) loads key for key into the native GaussianDiffusion; the vocoder checkpoint with weight-norm
+    keys loads through the reference's two-format rule (nsf_hifigan.py:38-52)."""
+    import os
+    from conftest import GOLDEN
+    from fish_diffusion_b200 import formats
+    cfg = golden_cfg["WN_SMALL"]
+    ck = torch.load(os.path.join(GOLDEN, "ref_ckpt_small.ckpt"), map_location="cpu", weights_only=False)
+    diff = DIFFUSIONS.build(dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **cfg), mel_channels=16,
+                                 spec_min=[-5.0], spec_max=[0.0]))
+    for part in ("model", "ema_model"):
+        sd = formats.lightning_state_dict(ck, part)
+        res = diff.load_state_dict({k[len("diffusion."):]: v for k, v in sd.items()}, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+    gsd = torch.load(os.path.join(GOLDEN, "ref_generator_small.ckpt"), map_location="cpu", weights_only=False)["generator"]
+    assert any(k.endswith("weight_g") or "parametrizations" in k for k in gsd)
+
+
+def test_oracle_ref_copy_is_verbatim():
+    """oracle/_ref (the files the CPU baseline runs) are byte-identical to /root/reference when both are present."""
+    import hashlib
+    import json as _json
+    import os
+    from oracle.ref_loader import REF_FILES
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not (os.path.isdir(here) and os.path.isdir("/root/reference")):
+        pytest.skip("needs both /root/reference and oracle/_ref")
+    man = _json.load(open(os.path.join(here, "MANIFEST.json")))["sha256"]
+    for rel in REF_FILES:
+        with open(os.path.join("/root/reference", rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == man[rel], rel
+        with open(os.path.join(here, rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == man[rel], rel
