@@ -115,8 +115,9 @@ class PitchAdjustableMelSpectrogram:
                 mel = mel_filterbank(self.sample_rate, self.n_fft, self.n_mels, self.f_min, self.f_max)
                 self.mel_basis[basis_key] = torch.from_numpy(mel).float().to(device)
             basis = self.mel_basis[basis_key]
-            W = torch.zeros((self.n_mels, self.NB), dtype=torch.float32, device=device)
-            W[:, :bins] = basis[:, :bins]       # bins beyond the (shrunk) spectrum are zero-padded by the reference
+            # rows padded to a multiple of 64 (zero rows) so that every n_mels has a tensor-core instantiation
+            W = torch.zeros(((self.n_mels + 63) // 64 * 64, self.NB), dtype=torch.float32, device=device)
+            W[:self.n_mels, :bins] = basis[:, :bins]   # bins beyond the (shrunk) spectrum are zero-padded by the reference
             s = N.pow2_scale(W)
             self._melw[key] = (N.pack_weight(W, prec, s), 1.0 / s)
         return self._melw[key]
@@ -172,13 +173,14 @@ class PitchAdjustableMelSpectrogram:
                                         self.NB, w_inv, mag_scale, mag_eps, N.mma_code(self.precision), self._backend(), st),
                 "fd_stft_mag_eps_fwd")
         mw, mw_inv = self._mel_weights(bins, dev, prec)
-        mel_cl = torch.empty((B, frames, self.n_mels), dtype=torch.float32, device=dev)
-        N.conv_cl(mag, mw, B, frames, self.NB, self.n_mels, [0], out_f32=mel_cl, w_inv_scale=mw_inv, prec=N.mma_code(self.precision),
+        n_pad = mw.shape[1]
+        mel_cl = torch.empty((B, frames, n_pad), dtype=torch.float32, device=dev)
+        N.conv_cl(mag, mw, B, frames, self.NB, n_pad, [0], out_f32=mel_cl, w_inv_scale=mw_inv, prec=N.mma_code(self.precision),
                   backend=self._backend())
-        out = torch.empty((B, self.n_mels, frames), dtype=torch.float32, device=dev)
-        N.check(lib.fd_transpose_nwc_to_ncw(N.ptr(mel_cl), N.ptr(out), B, frames, self.n_mels, st),
+        out = torch.empty((B, n_pad, frames), dtype=torch.float32, device=dev)
+        N.check(lib.fd_transpose_nwc_to_ncw(N.ptr(mel_cl), N.ptr(out), B, frames, n_pad, st),
                 "fd_transpose_nwc_to_ncw")
-        return out
+        return out if n_pad == self.n_mels else out[:, :self.n_mels].contiguous()
 
 
 class MelSpectrogram(PitchAdjustableMelSpectrogram):

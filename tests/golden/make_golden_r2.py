@@ -212,7 +212,7 @@ def gold_ckpt(ref, out):
             p.mul_(3.0)                     # init std 0.01 gives near-silent output; any deterministic weights do
     torch.save({"generator": gen.state_dict()}, os.path.join(HERE, "ref_generator_small.ckpt"))
     with open(os.path.join(HERE, "ref_generator_small.json"), "w") as f:
-        json.dump(mg.VOC_SMALL, f)
+        json.dump(dict(mg.VOC_SMALL, n_fft=256, win_size=256, fmin=40, fmax=16000), f)   # + the mel front-end keys
     gen.eval()
     gen.remove_weight_norm()
     mel = (rng.randn(1, h.num_mels, 20) - 2.5).clip(-11.5, 2).astype(np.float32)
