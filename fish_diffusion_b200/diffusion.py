@@ -204,8 +204,22 @@ class GaussianDiffusion(nn.Module):
         return self._affine(x, inverse=True)
 
     def _rng_seed(self):
+        """Philox key of the current call.  An explicit `seed=` wins; otherwise ONE int64 is drawn from torch's default
+        (CPU) generator at the start of every sampler / train_step call (`_begin_call`), so `torch.manual_seed(s)`
+        followed by the same calls reproduces the same outputs (as it does for the reference's torch.randn draws), two
+        consecutive calls differ, and a resumed run continues from the restored generator state.  Ranks that share a
+        torch seed draw the same key; their items are told apart by the global element index (first_item)."""
         s = getattr(self, "_seed_override", None)
-        return (int(s) if s is not None else int(torch.initial_seed())) & (2 ** 63 - 1)
+        if s is None:
+            s = getattr(self, "_call_seed", None)
+        if s is None:
+            s = self._begin_call()
+        return int(s) & (2 ** 63 - 1)
+
+    def _begin_call(self):
+        self._call_seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        self._philox_calls = 0
+        return self._call_seed
 
     def _sampler_ws(self, dev, B, T, M, E):
         key = (str(dev), B, T, M, E)
@@ -276,6 +290,7 @@ class GaussianDiffusion(nn.Module):
         dev = features.device
         prec = self._prec()
         self._subseq0 = 0
+        self._begin_call()
         if t is None:
             t = torch.randint(0, self.num_timesteps, (B,), device=dev).long()
         with torch.no_grad():
@@ -314,6 +329,8 @@ class GaussianDiffusion(nn.Module):
                                     x_masks, cond_masks, x_T, step_noises, None, first_item)
             finally:
                 self._seed_override = None
+        if getattr(self, "_seed_override", None) is None:
+            self._begin_call()
         if sampler_interval is None:
             sampler_interval = self.sampler_interval
         if noise_predictor is None:
@@ -337,8 +354,10 @@ class GaussianDiffusion(nn.Module):
             x = self._to_cl(x_T) if x_T is not None else self._randn((B, T, M), dev, out=ws["x"])
         else:
             # the reference passes original_mel as [B,M,T]-normalisable; it is normalised then used as x [B,M,T]
+            # the reference's own callers hand original_mel over as [B, M, T] (tools/diffusion/inference.py: the mel is
+            # transposed before the call); [B, T, M] is accepted only when the shape is unambiguous
             om = original_mel.to(torch.float32)
-            x = self.norm_spec(self._to_cl(om) if om.shape[1] == M and om.shape[2] == T else om)
+            x = self.norm_spec(self._to_cl(om) if om.shape[1] == M and (om.shape[2] == T or M != T) else om)
         if skip_steps:
             t0 = torch.tensor([self.num_timesteps - skip_steps], device=dev, dtype=torch.long)
             qn = self._to_cl(x_T) if (x_T is not None and original_mel is not None) else None

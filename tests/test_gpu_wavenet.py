@@ -150,6 +150,10 @@ def test_sampler_free_running_philox_statistics(golden, golden_cfg):
     b = diff(feats, sampler_interval=100, noise_predictor="naive")
     assert torch.isfinite(a).all() and float(a.min()) >= -5.0 - 1e-4 and float(a.max()) <= 1e-4
     assert not torch.equal(a, b)
+    torch.manual_seed(5)          # the Philox key is drawn from torch's generator: re-seeding reproduces both calls
+    a2 = diff(feats, sampler_interval=100, noise_predictor="naive")
+    b2 = diff(feats, sampler_interval=100, noise_predictor="naive")
+    assert torch.equal(a, a2) and torch.equal(b, b2)
 
 
 def test_randn_kernel_moments():
