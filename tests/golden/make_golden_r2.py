@@ -13,6 +13,8 @@ and the recorded-random machinery).  Run in the build container:  python tests/g
   r2_audio.npz       utils/audio.py get_mel_transform / get_mel_from_audio / dynamic_range_compression (torchaudio
                      MelSpectrogram variant used by the training losses); librosa / fish_audio_preprocess are stubbed,
                      the executed code path touches neither.
+  r2_diffsinger.npz  archs/diffsinger/diffsinger.py DiffSinger.forward_features / forward (+ NaiveProjectionEncoder,
+                     pitch_to_scale) with the un-importable Lightning-side names stubbed: features, masks, loss, encoder grads.
   ref_ckpt_small.ckpt / ref_generator_small.ckpt   checkpoints WRITTEN by the reference classes (state_dict of the
                      reference GaussianDiffusion under Lightning's `model.diffusion.` prefix with an `ema_model.` copy; the
                      reference Generator with weight-norm keys as {"generator": ...}) plus the reference outputs.
@@ -222,12 +224,103 @@ def gold_ckpt(ref, out):
     out["ck_voc_mel"], out["ck_voc_f0"], out["ck_voc_wav"], out["ck_voc_rseed"] = mel, f0, wav.numpy(), np.array(125)
 
 
+def gold_diffsinger(ref, out):
+    """archs/diffsinger/diffsinger.py `DiffSinger` (UNMODIFIED file) with NaiveProjectionEncoder and pitch_to_scale.  The file
+    needs loralib, matplotlib, pytorch_lightning, wandb, mmengine and package-level imports at import time only (for the
+    Lightning wrapper class further down the same file): those names are stubbed; the executed code is the reference's
+    `forward_features` / `forward`, its encoders (modules/encoders/naive_projection.py) and utils/pitch.py."""
+    class _Any:
+        def __getattr__(self, k):
+            return _Any()
+
+        def __call__(self, *a, **k):
+            return _Any()
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _LM(torch.nn.Module):
+        pass
+
+    stub("loralib")
+    stub("matplotlib"); stub("matplotlib.pyplot")
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    stub("pytorch_lightning", LightningModule=_LM)
+    stub("pytorch_lightning.loggers", TensorBoardLogger=_Any, WandbLogger=_Any)
+    stub("wandb")
+    stub("mmengine"); stub("mmengine.optim", OPTIMIZERS=_Any())
+    enc_reg = mg._MiniRegistry("encoders")
+    pkg = types.ModuleType("refenc2"); pkg.__path__ = [f"{REF}/fish_diffusion/modules/encoders"]; sys.modules["refenc2"] = pkg
+    stub("refenc2.builder", ENCODERS=enc_reg)
+    npj = mg._load("refenc2.naive_projection", f"{REF}/fish_diffusion/modules/encoders/naive_projection.py", "refenc2")
+    pitch = mg._load("ref_pitch_utils", f"{REF}/fish_diffusion/utils/pitch.py")
+    stub("fish_diffusion"); stub("fish_diffusion.modules")
+    stub("fish_diffusion.modules.encoders", ENCODERS=enc_reg)
+    stub("fish_diffusion.modules.vocoders", VOCODERS=_Any())
+    stub("fish_diffusion.modules.vocoders.builder", VOCODERS=_Any())
+    stub("fish_diffusion.schedulers", LR_SCHEUDLERS=_Any())
+    stub("fish_diffusion.utils"); stub("fish_diffusion.utils.viz", viz_synth_sample=_Any())
+    dpkg = types.ModuleType("refds"); dpkg.__path__ = [f"{REF}/fish_diffusion/archs/diffsinger"]; sys.modules["refds"] = dpkg
+    diff_reg = mg._MiniRegistry("diffusions")
+    diff_reg.register_module(name="GaussianDiffusion", module=ref.diffusion.GaussianDiffusion)
+    stub("refds.diffusions", DIFFUSIONS=diff_reg)
+    stub("refds.grad_tts", GradTTS=_Any)
+    ds = mg._load("refds.diffsinger", f"{REF}/fish_diffusion/archs/diffsinger/diffsinger.py", "refds")
+
+    class Cfg(dict):
+        __getattr__ = dict.get
+
+    wn = mg.WN_SMALL
+    E, M = wn["d_encoder"], wn["mel_channels"]
+    cfg = Cfg(text_encoder=dict(type="NaiveProjectionEncoder", input_size=24, output_size=E),
+              speaker_encoder=dict(type="NaiveProjectionEncoder", input_size=5, output_size=E, use_embedding=True),
+              pitch_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E, preprocessing=pitch.pitch_to_scale),
+              pitch_shift_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E, use_neck=True, neck_size=4),
+              energy_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E),
+              diffusion=dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **wn), mel_channels=M,
+                             noise_loss="smoothed-l1", sampler_interval=10, spec_min=[-5.0], spec_max=[0.0]))
+    torch.manual_seed(301)
+    model = ds.DiffSinger(cfg)
+    torch.nn.init.kaiming_normal_(model.diffusion.denoise_fn.output_projection.conv.weight)
+    for k, v in model.state_dict().items():
+        out["ds_sd_" + k] = v.numpy()
+    rng = np.random.RandomState(302)
+    B, T = 3, 37
+    lens = torch.tensor([37, 20, 29])
+    contents = torch.from_numpy(rng.randn(B, T, 24).astype(np.float32))
+    pitches = torch.from_numpy((rng.rand(B, T).astype(np.float32) * 900 + 40))
+    speakers = torch.tensor([0, 3, 4])
+    pitch_shift = torch.from_numpy(rng.randn(B, 1).astype(np.float32))
+    energy = torch.from_numpy(rng.rand(B, T, 1).astype(np.float32))
+    with torch.no_grad():
+        f = model.forward_features(speakers=speakers, contents=contents, contents_lens=lens, contents_max_len=T,
+                                   mel_lens=lens, mel_max_len=T, pitches=pitches.clone(), pitch_shift=pitch_shift, energy=energy)
+    out["ds_contents"], out["ds_pitches"], out["ds_speakers"], out["ds_lens"] = contents.numpy(), pitches.numpy(), speakers.numpy(), lens.numpy()
+    out["ds_pitch_shift"], out["ds_energy"] = pitch_shift.numpy(), energy.numpy()
+    out["ds_features"], out["ds_x_masks"] = f["features"].numpy(), f["x_masks"].numpy()
+    mel = torch.from_numpy((rng.rand(B, T, M).astype(np.float32) * 5 - 5))
+    with mg.RecordedRandom(303) as rr:
+        torch.manual_seed(304)                      # randint(t) comes from torch's own generator
+        o = model(speakers=speakers, contents=contents, contents_lens=lens, contents_max_len=T, mel=mel, mel_lens=lens,
+                  mel_max_len=T, pitches=pitches.clone(), pitch_shift=pitch_shift, energy=energy)
+    o["loss"].backward()
+    out["ds_mel"], out["ds_t"], out["ds_loss"] = mel.numpy(), o["t"].numpy(), o["loss"].detach().numpy()
+    out["ds_noise"] = rr.log[0][1]                  # randn_like(x) of train_step, [B, M, T]
+    out["ds_g_text_w"] = model.text_encoder.projection.weight.grad.numpy()
+    out["ds_g_pitch_w"] = model.pitch_encoder.projection.weight.grad.numpy()
+    out["ds_g_spk_w"] = model.speaker_encoder.embedding.weight.grad.numpy()
+    print(f"  diffsinger: features {tuple(f['features'].shape)}, loss {float(o['loss']):.5f}, draws {[k for k, _ in rr.log]}")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = mg.load_reference()
     groups = {"traj": gold_traj, "train_full": gold_train_full, "train_masked": gold_train_masked, "voc": gold_voc,
-              "audio": gold_audio, "ckpt": gold_ckpt}
+              "audio": gold_audio, "ckpt": gold_ckpt, "diffsinger": gold_diffsinger}
     only = sys.argv[1:]
     for name, fn in groups.items():
         if only and name not in only:

@@ -192,3 +192,43 @@ def test_checkpoints_written_by_reference_classes(golden, golden_cfg):
     nz = rng.randn(B, T * voc.h["hop_size"], 9).astype(np.float32)
     wav = voc.model(T_(mel), T_(f0), rand_ini=T_(ri), sine_noise=T_(nz)).cpu().numpy()
     assert rel_l2(wav, g["ck_voc_wav"]) < 1e-4
+
+
+# ------------------------------------------------------------------ DiffSinger assembly (a21 / N1)
+def test_diffsinger_forward_features_and_train_step_vs_reference(golden, golden_cfg):
+    """archs/diffsinger/diffsinger.py DiffSinger.forward_features / forward of the UNMODIFIED reference (r2_diffsinger.npz):
+    same state_dict keys, features and masks, and the training loss + encoder gradients through the native backward (the
+    gradient w.r.t. the features is what flows back into the projections)."""
+    from fish_diffusion_b200 import DiffSinger, pitch_to_scale
+    g = golden("r2_diffsinger")
+    wn = golden_cfg["WN_SMALL"]
+    E, M = wn["d_encoder"], wn["mel_channels"]
+    cfg = dict(text_encoder=dict(type="NaiveProjectionEncoder", input_size=24, output_size=E),
+               speaker_encoder=dict(type="NaiveProjectionEncoder", input_size=5, output_size=E, use_embedding=True),
+               pitch_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E, preprocessing=pitch_to_scale),
+               pitch_shift_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E, use_neck=True, neck_size=4),
+               energy_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E),
+               diffusion=dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **wn), mel_channels=M,
+                              noise_loss="smoothed-l1", sampler_interval=10, spec_min=[-5.0], spec_max=[0.0]))
+    model = DiffSinger(cfg)
+    sd = {k[len("ds_sd_"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("ds_sd_")}
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    model = model.to(dev()).train()
+    lens = T_(g["ds_lens"])
+    Tm = int(g["ds_contents"].shape[1])
+    kw = dict(speakers=T_(g["ds_speakers"]), contents=T_(g["ds_contents"]), contents_lens=lens, contents_max_len=Tm,
+              mel_lens=lens, mel_max_len=Tm, pitches=T_(g["ds_pitches"]), pitch_shift=T_(g["ds_pitch_shift"]),
+              energy=T_(g["ds_energy"]))
+    f = model.forward_features(**kw)
+    assert rel_l2(f["features"].detach().cpu().numpy(), g["ds_features"]) < 1e-6
+    assert np.array_equal(f["x_masks"].cpu().numpy(), g["ds_x_masks"]) and f["cond_masks"] is f["x_masks"]
+    out = model.diffusion.train_step(f["features"], T_(g["ds_mel"]), x_masks=f["x_masks"], cond_masks=f["cond_masks"],
+                                     t=T_(g["ds_t"]), noise=T_(g["ds_noise"]))
+    assert abs(float(out["loss"]) - float(g["ds_loss"])) < 2e-5 * abs(float(g["ds_loss"]))
+    out["loss"].backward()
+    for name, p in (("text_w", model.text_encoder.projection.weight), ("pitch_w", model.pitch_encoder.projection.weight),
+                    ("spk_w", model.speaker_encoder.embedding.weight)):
+        e = rel_l2(p.grad.cpu().numpy(), g[f"ds_g_{name}"])
+        print(f"DiffSinger encoder gradient {name}: rel-L2 vs the reference autograd {e:.2e}")
+        assert e < 2e-4
