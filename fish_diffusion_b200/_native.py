@@ -49,6 +49,7 @@ class GemmDesc(ctypes.Structure):
         ("row_mask", c_void_p), ("out_f32", c_void_p), ("out_planes", c_void_p),
         ("w_inv_scale", c_float), ("res_scale", c_float), ("post_scale", c_float), ("planes_scale", c_float),
         ("act_slope", c_float), ("out_accum", c_int), ("act", c_int), ("prec", c_int), ("backend", c_int),
+        ("bias_bstride", c_int),
     ]
 
 
@@ -369,7 +370,7 @@ def tc_supported_linear(n_total: int, k_seg: int, num_seg: int) -> bool:
 
 
 def gemm_cl(src0, C0, w_planes, n_total, k_total, B, T, segs, *, src1=None, C1=0, strides0=None, strides1=None,
-            w_kshift=0, w_bstride_k=0, bias=None, addend=None, res_f32=None, res_planes=None, res_scale=1.0,
+            w_kshift=0, w_bstride_k=0, bias=None, bias_per_item=False, addend=None, res_f32=None, res_planes=None, res_scale=1.0,
             row_mask=None, out_f32=None, out_planes=None, w_inv_scale=1.0, post_scale=1.0, planes_scale=1.0,
             act=ACT_NONE, act_slope=0.0, out_accum=False, prec=PREC_F16, backend=BACKEND_TC):
     """General linear tap-GEMM (fd_gemm_cl_fwd).  segs = [(src_index, shift, c_off, k_len), ...];
@@ -389,6 +390,7 @@ def gemm_cl(src0, C0, w_planes, n_total, k_total, B, T, segs, *, src1=None, C1=0
     d.w_inv_scale, d.res_scale, d.post_scale = w_inv_scale, res_scale, post_scale
     d.planes_scale, d.act_slope = planes_scale, act_slope
     d.out_accum, d.act, d.prec, d.backend = int(out_accum), act, prec, backend
+    d.bias_bstride = n_total if bias_per_item else 0
     check(lib().fd_gemm_cl_fwd(ctypes.byref(d), stream_ptr(src0.device)), "fd_gemm_cl_fwd")
 
 

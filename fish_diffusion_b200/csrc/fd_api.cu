@@ -330,7 +330,7 @@ int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream) {
   FD_REQUIRE(p.src[0] != nullptr, "fd_gemm_cl_fwd: src[0] is null");
   p.w = d->w; p.acc_scale = d->w_inv_scale; p.w_kshift = d->w_kshift; p.w_bstride_k = d->w_bstride_k;
   p.epi = FD_EPI_LINEAR;
-  p.bias = d->bias; p.bias_bstride = 0;
+  p.bias = d->bias; p.bias_bstride = d->bias_bstride;
   p.addend = d->addend; p.res_f32 = d->res_f32; p.res_planes = d->res_planes; p.res_scale = d->res_scale;
   p.post_scale = d->post_scale; p.out_f32 = d->out_f32; p.out_accum = d->out_accum;
   p.out_planes = d->out_planes; p.planes_scale = d->planes_scale; p.act = d->act; p.act_slope = d->act_slope;

@@ -314,19 +314,22 @@ class GaussianDiffusion(nn.Module):
     def forward(self, features, sampler_interval=None, progress: bool = False, skip_steps: int = 0,
                 original_mel: torch.Tensor = None, noise_predictor: str = None, x_masks: torch.Tensor = None,
                 cond_masks: torch.Tensor = None, x_T: torch.Tensor = None, step_noises=None, seed: int = None,
-                first_item: int = 0):
+                first_item: int = 0, cond_planes: torch.Tensor = None):
         """Reference contract (diffusion.py:196-313): features [B,T,E] -> mel [B,T,M].
         Extra (parity tests): x_T [B,M,T] replaces the initial randn / the q_sample noise of shallow diffusion,
         step_noises[i] [B,M,T] replaces the i-th randn_like of the naive predictor.
         first_item: index of features[0] inside the global batch.  The in-kernel Philox draws are indexed by the
         global element, so with the same `seed` a batch sharded over ranks / split into calls of
-        the same T reproduces the unsharded result bit for bit."""
+        the same T reproduces the unsharded result bit for bit.
+        cond_planes: the conditioner already as split planes [2,B,T,E] (DiffSinger.conditioner_planes: the feature
+        projections written straight into the sampler's plane buffer by one GEMM); `features` may then be None and
+        `cond_masks` must already have been applied."""
         if seed is not None:
             # reproducible call: Philox streams are (seed, draw index within this call) instead of the running counter
             self._seed_override, self._philox_calls = int(seed), 0
             try:
                 return self.forward(features, sampler_interval, progress, skip_steps, original_mel, noise_predictor,
-                                    x_masks, cond_masks, x_T, step_noises, None, first_item)
+                                    x_masks, cond_masks, x_T, step_noises, None, first_item, cond_planes)
             finally:
                 self._seed_override = None
         if getattr(self, "_seed_override", None) is None:
@@ -338,18 +341,22 @@ class GaussianDiffusion(nn.Module):
         noise_predictor = noise_predictor.lower()
         if noise_predictor not in ("naive", "unipc", "plms"):
             raise NotImplementedError(f"Unknown noise predictor: {noise_predictor}")
-        N.require_cuda(features, "features")
-        dev = features.device
+        N.require_cuda(features if cond_planes is None else cond_planes, "features")
+        dev = (features if cond_planes is None else cond_planes).device
         den = self.denoise_fn
         prec = self._prec()
-        B, T, E = features.shape
+        B, T, E = features.shape if cond_planes is None else tuple(cond_planes.shape[1:])
         M = self.mel_bins
         self._subseq0 = int(first_item) * ((T * M + 3) // 4)      # first Philox subsequence (one per 4 elements)
         cmask = None if cond_masks is None else cond_masks.to(torch.uint8).contiguous()
         # per-shape work buffers are kept between calls: stable pointers let the denoiser replay its captured CUDA
         # graph from the first evaluation of every later call (one in-flight sampler call per module instance)
         ws = self._sampler_ws(dev, B, T, M, E)
-        cond_planes = N.split_nwc(features.to(torch.float32), prec, mask=cmask, out=ws["cond_planes"])   # once per call
+        if cond_planes is None:
+            cond_planes = N.split_nwc(features.to(torch.float32), prec, mask=cmask, out=ws["cond_planes"])   # once per call
+        elif cond_planes.data_ptr() != ws["cond_planes"].data_ptr():
+            ws["cond_planes"].copy_(cond_planes)
+            cond_planes = ws["cond_planes"]
         if original_mel is None:
             x = self._to_cl(x_T) if x_T is not None else self._randn((B, T, M), dev, out=ws["x"])
         else:

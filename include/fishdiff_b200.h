@@ -282,6 +282,8 @@ typedef struct fd_gemm_desc {
   uint16_t* out_planes;
   float w_inv_scale, res_scale, post_scale, planes_scale, act_slope;
   int out_accum, act, prec, backend;
+  int bias_bstride;   /* 0: bias [n_total]; n_total: one bias vector per batch item, bias [B][n_total] (per-utterance
+                         speaker / pitch-shift embeddings of DiffSinger.forward_features, diffsinger.py:95-121) */
 } fd_gemm_desc;
 int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream);
 

@@ -232,3 +232,40 @@ def test_diffsinger_forward_features_and_train_step_vs_reference(golden, golden_
         e = rel_l2(p.grad.cpu().numpy(), g[f"ds_g_{name}"])
         print(f"DiffSinger encoder gradient {name}: rel-L2 vs the reference autograd {e:.2e}")
         assert e < 2e-4
+
+
+def test_diffsinger_fused_conditioner_planes(golden, golden_cfg):
+    """The feature projections as ONE GEMM writing the sampler's conditioner planes (DiffSinger.conditioner_planes) equal the
+    reference's forward_features followed by the masked split, and the sampler gives the same mel from either."""
+    from fish_diffusion_b200 import DiffSinger, pitch_to_scale, _native as N
+    from gpu_util import planes_to_f64
+    g = golden("r2_diffsinger")
+    wn = golden_cfg["WN_SMALL"]
+    E, M = wn["d_encoder"], wn["mel_channels"]
+    cfg = dict(text_encoder=dict(type="NaiveProjectionEncoder", input_size=24, output_size=E),
+               speaker_encoder=dict(type="NaiveProjectionEncoder", input_size=5, output_size=E, use_embedding=True),
+               pitch_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E, preprocessing=pitch_to_scale),
+               pitch_shift_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E, use_neck=True, neck_size=4),
+               energy_encoder=dict(type="NaiveProjectionEncoder", input_size=1, output_size=E),
+               diffusion=dict(type="GaussianDiffusion", denoiser=dict(type="WaveNetDenoiser", **wn), mel_channels=M,
+                              noise_loss="smoothed-l1", sampler_interval=100, spec_min=[-5.0], spec_max=[0.0]))
+    model = DiffSinger(cfg)
+    model.load_state_dict({k[len("ds_sd_"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("ds_sd_")})
+    model = model.to(dev()).eval()
+    lens = T_(g["ds_lens"])
+    Tm = int(g["ds_contents"].shape[1])
+    kw = dict(speakers=T_(g["ds_speakers"]), contents=T_(g["ds_contents"]), contents_lens=lens, contents_max_len=Tm,
+              mel_lens=lens, mel_max_len=Tm, pitches=T_(g["ds_pitches"]), pitch_shift=T_(g["ds_pitch_shift"]),
+              energy=T_(g["ds_energy"]))
+    assert model._fusable()
+    f = model.conditioner_planes(**kw)
+    want = g["ds_features"].astype(np.float64).copy()
+    want[g["ds_x_masks"]] = 0.0                                 # cond_masks masked_fill (wavenet.py:220-221)
+    got = planes_to_f64(f["cond_planes"], N.PREC_F16)
+    assert rel_l2(got, want) < 2e-6
+    with torch.no_grad():
+        ff = model.forward_features(**{**kw, "pitches": T_(g["ds_pitches"])})
+        mel_a = model.diffusion(ff["features"], x_masks=ff["x_masks"], cond_masks=ff["cond_masks"], sampler_interval=100,
+                                noise_predictor="naive", seed=9)
+        mel_b = model.synthesize(**{**kw, "pitches": T_(g["ds_pitches"])}, sampler_interval=100, noise_predictor="naive", seed=9)
+    assert rel_l2(mel_b.cpu().numpy(), mel_a.cpu().numpy()) < 1e-5
