@@ -604,6 +604,7 @@ void pick_cfg(const FdTapGemm& p, int* bn, int* bk) {
     return;
   }
   int n = 256;
+  // (GEMM2 with narrower column tiles was measured in round 2: 256 -> 0.406 ms, 128 -> 0.426 ms, 64 -> 0.667 ms per launch)
   while (n >= 16 && (p.n_total % n != 0 || (p.epi == FD_EPI_RES_SKIP && p.C % n != 0))) n >>= 1;
   if (n < 16) return;
   if (k == 64) {
