@@ -24,6 +24,7 @@
 // Warp roles (persistent, one CTA per SM): 0 = weight TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
 // 3 = activation-tile TMA producer, 4.. = epilogue (8 warps; 4 at C = 16).
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #include "fd_common.cuh"
 #include "fd_host.h"
@@ -33,6 +34,16 @@
 // non-overlapped epilogue; measured 16.1 -> 15.1 ms for k = 11), 8 below (measured slower with 16: 3.13 -> 3.9 ms)
 #ifndef FD_RP_EPI_WARPS
 #define FD_RP_EPI_WARPS(C) ((C) >= 128 ? 16 : 8)
+#endif
+// MCAST: the kernel runs as clusters of two CTAs that share ONE weight stream: each CTA loads one plane (hi or lo) of
+// every weight unit and multicasts it into both CTAs' rings, and a stage is released when both CTAs' MMA warps have
+// committed it.  Halves the L2 -> shared-memory weight traffic at C = 128 (one 128-row block per tile, the pair's
+// 1.4 MB of weights per tile at k = 11; ncu: 106.7 GB of TMA loads per launch).  Measured: 1-3 % (15.1 -> 14.9 ms for
+// k = 11) -- the weight stream was not the limiter; neither was the depth of the ring (4 / 6 / 8 stages: same time).  What
+// was: the per-stage handshake of the single issuing thread (barrier wait, fences, commit) against the 4 MMAs of a 16 KB
+// stage -- 32 KB stages (2 x GROUP units, launch_respair) took k = 7 from 11.1 to 9.5 ms on the same box.
+#ifndef FD_RP_MCAST
+#define FD_RP_MCAST(C) ((C) == 128)
 #endif
 #ifndef FD_RP_STAGE_MAJOR
 #define FD_RP_STAGE_MAJOR(C) ((C) == 64 || (C) == 32)
@@ -46,6 +57,9 @@ struct FdResPairK {
   int h1, h2;        // halos of c1 / c2 in rows
   int r_in, rb, nbox;   // rows of the input tile = nbox TMA boxes of rb rows (rb a multiple of 8)
   int r_out;         // valid output rows per tile = MB*128 - (k2-1)
+  int nstages;       // stages of the weight ring (what the input tile of this launch leaves free)
+  int group;         // weight units per stage of the ring
+  int in_alloc_rows; // rows reserved per plane of the input tile (r_in, or RIN_MAX with the fixed layout)
   int single;        // one product (hi planes only)
   float inv_s1, inv_s2, s2;
   float in_slope_inv, out_slope, planes_scale;
@@ -77,9 +91,9 @@ struct RpCfg {
   static constexpr int GROUP_RAW = 16384 / UNIT_BYTES;
   static constexpr int GROUP = GROUP_RAW > 8 ? 8 : GROUP_RAW;   // weight units per pipeline stage
   static constexpr int STAGE_BYTES = GROUP * UNIT_BYTES;
-  static constexpr int IN_PLANE_BYTES = RIN_MAX * ROWB;
-  static constexpr int IN_KB_BYTES = 2 * IN_PLANE_BYTES;
-  static constexpr int IN_BYTES = NKB * IN_KB_BYTES;
+  // the input tile is sized per launch (in_plane = r_in * ROWB bytes per plane): what a small halo leaves free becomes
+  // extra stages of the weight ring (at C = 128 three stages for k = 11, d = 5 but five for the d = 1 pairs)
+  static constexpr int IN_PLANE_BYTES_MAX = RIN_MAX * ROWB;
   static constexpr int MID_PLANE_BYTES = MID_ROWS * ROWB;
   static constexpr int MID_KB_BYTES = 2 * MID_PLANE_BYTES;
   static constexpr int MID_BYTES = NKB * MID_KB_BYTES;     // c1 output; afterwards the staging image of the output
@@ -88,6 +102,7 @@ struct RpCfg {
   // C = 32 / 64); the price is that the blocks of a tile finish a GEMM together, so their epilogues no longer overlap
   // the MMAs of the following blocks.
   static constexpr bool STAGE_MAJOR = FD_RP_STAGE_MAJOR(C);
+  static constexpr bool MCAST = FD_RP_MCAST(C);
   static constexpr int EPI_WARPS = FD_RP_EPI_WARPS(C);
   static constexpr int HALVES_WANT = C >= 128 ? 4 : C >= 32 ? 2 : 1;
   static constexpr int HALVES = HALVES_WANT > EPI_WARPS / 4 ? EPI_WARPS / 4 : HALVES_WANT;   // column split of a block
@@ -98,13 +113,17 @@ struct RpCfg {
   static constexpr int THREADS = 128 + EPI_THREADS;
   static constexpr int TMEM_COLS = 512;                     // acc1[j] at j*2C, acc2[j] at 256 + j*2C
   static constexpr int NBAR = 2 + 3 * MB;
-  static constexpr int FIXED = 1024 + IN_BYTES + MID_BYTES + 2 * C * 4 + (NBAR + 16) * 8 + 64;
-  static constexpr int RAW_STAGES = (227 * 1024 - FIXED) / STAGE_BYTES;
-  static constexpr int NUM_STAGES = RAW_STAGES > 6 ? 6 : RAW_STAGES;
-  static constexpr int SMEM_BYTES = FIXED + NUM_STAGES * STAGE_BYTES;
-  static_assert(NUM_STAGES >= 2, "weight ring needs two stages");
-  static_assert(IN_PLANE_BYTES % 1024 == 0 || (ROWB == 64 && IN_PLANE_BYTES % 512 == 0) || (ROWB == 32 && IN_PLANE_BYTES % 256 == 0),
-                "plane regions must start on a swizzle-pattern boundary");
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int HEAD_BYTES = 2048;                   // biases (2C floats <= 1 KB) + barriers, in front of the tiles
+  static constexpr int SMEM_BYTES = 227 * 1024;             // always the whole shared memory: the ring takes what is left
+  static constexpr int FIXED_MAX = 1024 + HEAD_BYTES + NKB * 2 * IN_PLANE_BYTES_MAX + MID_BYTES;
+  static_assert((SMEM_BYTES - FIXED_MAX) / STAGE_BYTES >= 2, "weight ring needs two stages");
+  static_assert(2 * C * 4 + (2 * MAX_STAGES + NBAR + 2) * 8 + 16 <= HEAD_BYTES, "head region too small");
+  // stages of the weight ring for an input tile of r_in rows
+  static constexpr int stages_for(int r_in, int group) {
+    const int n = (SMEM_BYTES - 1024 - HEAD_BYTES - NKB * 2 * r_in * ROWB - MID_BYTES) / (group * UNIT_BYTES);
+    return n > MAX_STAGES ? MAX_STAGES : n;
+  }
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -116,6 +135,29 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n" : "=r"(pred));
   return pred != 0;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one plane of a weight unit, written into the same shared-memory offset of BOTH CTAs of the pair; the transaction bytes
+// are signalled on the barrier at the same offset in each destination CTA
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
@@ -156,13 +198,18 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   constexpr int MB = K::MB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* in_s = smem;
-  uint8_t* mid_s = in_s + K::IN_BYTES;
-  uint8_t* w_s = mid_s + K::MID_BYTES;
-  float* bias_s = reinterpret_cast<float*>(w_s + K::NUM_STAGES * K::STAGE_BYTES);   // b1 [C] | b2 [C]
+  float* bias_s = reinterpret_cast<float*>(smem);                  // b1 [C] | b2 [C]
   uint64_t* w_full = reinterpret_cast<uint64_t*>(bias_s + 2 * C);
-  uint64_t* w_empty = w_full + K::NUM_STAGES;
-  uint64_t* in_full = w_empty + K::NUM_STAGES;
+  uint64_t* w_empty = w_full + K::MAX_STAGES;
+  uint64_t* in_full = w_empty + K::MAX_STAGES;
+  const int in_plane = p.in_alloc_rows * K::ROWB;                  // multiple of the swizzle period (rows % 8 == 0)
+  const int in_kb = 2 * in_plane;
+  const int NUM_STAGES = p.nstages;
+  const int GROUP = p.group;                                       // weight units per ring stage
+  const int STAGE_BYTES_RT = GROUP * K::UNIT_BYTES;
+  uint8_t* in_s = smem + K::HEAD_BYTES;
+  uint8_t* mid_s = in_s + K::NKB * in_kb;
+  uint8_t* w_s = mid_s + K::MID_BYTES;
   uint64_t* in_empty = in_full + 1;
   uint64_t* acc1_full = in_empty + 1;      // [MB]
   uint64_t* mid_ready = acc1_full + MB;    // [MB]
@@ -178,7 +225,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     prefetch_tmap(&tm_in); prefetch_tmap(&tm_w1); prefetch_tmap(&tm_w2); prefetch_tmap(&tm_out); prefetch_tmap(&tm_out_last);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < K::NUM_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], K::MCAST ? 2 : 1); }
     mbar_init(in_full, 1); mbar_init(in_empty, K::EPI_WARPS);
     for (int j = 0; j < MB; ++j) {
       mbar_init(&acc1_full[j], 1); mbar_init(&mid_ready[j], K::EPI_WARPS / K::GROUPS); mbar_init(&acc2_full[j], 1);
@@ -198,9 +245,14 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (K::MCAST) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+  // every CTA runs the same number of iterations (the pair shares the weight ring); iterations past the last tile only
+  // keep the ring turning
+  const int iters = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = K::MCAST ? cluster_ctarank() : 0u;
 
   const int units1 = p.k1 * K::UNITS_PER_TAP, units2 = p.k2 * K::UNITS_PER_TAP;
 
@@ -208,22 +260,26 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     // =========================================================== weight producer (the pair's weights, once per block)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < iters; ++it) {
         for (int g2 = 0; g2 < 2; ++g2) {
           const CUtensorMap* tm = g2 == 0 ? &tm_w1 : &tm_w2;
           const int units = g2 == 0 ? units1 : units2;
           for (int j = 0; j < (K::STAGE_MAJOR ? 1 : MB); ++j) {
-            for (int u0 = 0; u0 < units; u0 += K::GROUP) {
-              const int nb = min(K::GROUP, units - u0);
+            for (int u0 = 0; u0 < units; u0 += GROUP) {
+              const int nb = min(GROUP, units - u0);
               mbar_wait(&w_empty[stage], phase ^ 1);
               mbar_expect_tx(&w_full[stage], nb * K::UNIT_BYTES);
-              uint8_t* slot = w_s + stage * K::STAGE_BYTES;
+              uint8_t* slot = w_s + stage * STAGE_BYTES_RT;
               for (int g = 0; g < nb; ++g) {
                 const int u = u0 + g;
                 const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
-                tma_load_3d(slot + g * K::UNIT_BYTES, tm, &w_full[stage], tap * C + kw * K::BKW, 0, 0);
+                if (K::MCAST)     // this CTA's plane of the unit, into both CTAs
+                  tma_load_3d_mcast(slot + g * K::UNIT_BYTES + crank * (C * K::WROWB), tm, &w_full[stage],
+                                    tap * C + kw * K::BKW, 0, (int)crank, (uint16_t)3);
+                else
+                  tma_load_3d(slot + g * K::UNIT_BYTES, tm, &w_full[stage], tap * C + kw * K::BKW, 0, 0);
               }
-              if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -233,14 +289,14 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     // =========================================================== activation-tile producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {     // valid tiles only
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * p.r_out;
         mbar_wait(in_empty, (it & 1) ^ 1);
         mbar_expect_tx(in_full, K::NKB * 2 * p.r_in * K::ROWB);
         for (int kb = 0; kb < K::NKB; ++kb)
           for (int pl = 0; pl < 2; ++pl)
             for (int bx = 0; bx < p.nbox; ++bx)
-              tma_load_4d(in_s + kb * K::IN_KB_BYTES + pl * K::IN_PLANE_BYTES + bx * p.rb * K::ROWB, &tm_in, in_full,
+              tma_load_4d(in_s + kb * in_kb + pl * in_plane + bx * p.rb * K::ROWB, &tm_in, in_full,
                           kb * K::BK_A, t0 - p.h2 - p.h1 + bx * p.rb, b, pl);
       }
     }
@@ -259,14 +315,25 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     constexpr uint64_t DESC_HI_W = ((uint64_t)((SBO_W >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)K::LT_W << 61) | ((uint64_t)1 << 16);
     const bool single = p.single != 0;
     int stage = 0; uint32_t phase = 0;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0; it < (uint32_t)iters; ++it) {
+      const bool valid = (int)blockIdx.x + (int)it * (int)gridDim.x < num_tiles;
+      if (!valid) {     // no tile left for this CTA: consume and release the shared weight stages only
+        const int stages_per_tile = ((units1 + GROUP - 1) / GROUP + (units2 + GROUP - 1) / GROUP) *
+                                    (K::STAGE_MAJOR ? 1 : MB);
+        for (int sidx = 0; sidx < stages_per_tile; ++sidx) {
+          mbar_wait(&w_full[stage], phase);
+          if (elect_one()) { if (K::MCAST) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
+          __syncwarp();
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int g2 = 0; g2 < 2; ++g2) {
         const int units = g2 == 0 ? units1 : units2;
         const uint32_t a_base = g2 == 0 ? smem_u32(in_s) : smem_u32(mid_s);
-        const uint32_t a_kb = g2 == 0 ? K::IN_KB_BYTES : K::MID_KB_BYTES;
-        const uint32_t a_plane = g2 == 0 ? (uint32_t)K::IN_PLANE_BYTES : (uint32_t)K::MID_PLANE_BYTES;
+        const uint32_t a_kb = g2 == 0 ? in_kb : K::MID_KB_BYTES;
+        const uint32_t a_plane = g2 == 0 ? (uint32_t)in_plane : (uint32_t)K::MID_PLANE_BYTES;
         const uint32_t tap_bytes = (uint32_t)(g2 == 0 ? p.d1 : 1) * K::ROWB;
         if (g2 == 0) { mbar_wait(in_full, it & 1); tc_fence_after(); }
         if (K::STAGE_MAJOR) {
@@ -277,11 +344,11 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           }
           int u = 0;
 #pragma unroll 1
-          for (int u0 = 0; u0 < units; u0 += K::GROUP) {
-            const int nb = min(K::GROUP, units - u0);
+          for (int u0 = 0; u0 < units; u0 += GROUP) {
+            const int nb = min(GROUP, units - u0);
             mbar_wait(&w_full[stage], phase);
             tc_fence_after();
-            const uint32_t w_stage = smem_u32(w_s + stage * K::STAGE_BYTES);
+            const uint32_t w_stage = smem_u32(w_s + stage * STAGE_BYTES_RT);
 #pragma unroll 1
             for (int g = 0; g < nb; ++g, ++u) {
               const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
@@ -310,9 +377,9 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
               }
               __syncwarp();
             }
-            if (elect_one()) umma_commit(&w_empty[stage]);
+            if (elect_one()) { if (K::MCAST) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
             __syncwarp();
-            if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           }
           if (elect_one()) {
             for (int j = 0; j < MB; ++j) umma_commit(g2 == 0 ? &acc1_full[j] : &acc2_full[j]);
@@ -328,11 +395,11 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           }
           int u = 0;
 #pragma unroll 1
-          for (int u0 = 0; u0 < units; u0 += K::GROUP) {
-            const int nb = min(K::GROUP, units - u0);
+          for (int u0 = 0; u0 < units; u0 += GROUP) {
+            const int nb = min(GROUP, units - u0);
             mbar_wait(&w_full[stage], phase);
             tc_fence_after();
-            const uint32_t w_stage = smem_u32(w_s + stage * K::STAGE_BYTES);
+            const uint32_t w_stage = smem_u32(w_s + stage * STAGE_BYTES_RT);
 #pragma unroll 1
             for (int g = 0; g < nb; ++g, ++u) {
               const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
@@ -357,9 +424,9 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
               }
               __syncwarp();
             }
-            if (elect_one()) umma_commit(&w_empty[stage]);
+            if (elect_one()) { if (K::MCAST) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
             __syncwarp();
-            if (++stage == K::NUM_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           }
           if (elect_one()) umma_commit(g2 == 0 ? &acc1_full[j] : &acc2_full[j]);
           __syncwarp();
@@ -402,12 +469,12 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
             const int col = col_base + c16 * 16;
             const int kb = col / K::BK_A, cc = col % K::BK_A;
-            const uint32_t base = in_u + kb * K::IN_KB_BYTES;
+            const uint32_t base = in_u + kb * in_kb;
             float v[16];
 #pragma unroll
             for (int hq = 0; hq < 2; ++hq) {
               const uint32_t off = swz((uint32_t)n * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
-              const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + K::IN_PLANE_BYTES + off);
+              const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + in_plane + off);
               const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
@@ -523,6 +590,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (K::MCAST) cluster_sync_all();      // no multicast write / remote arrive may target a CTA that has exited
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS)
@@ -552,13 +620,13 @@ int make_planes_map(CUtensorMap* m, const uint16_t* ptr, int B, int T, int C, in
   return 0;
 }
 
-// packed weights [2][C][K] (uint16): box {bkw, C, 2}
-int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw) {
+// packed weights [2][C][K] (uint16): box {bkw, C, planes} (both planes of a unit, or one per CTA of a multicast pair)
+int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw, int planes) {
   PFN_tmapEncodeTiled enc = get_encode();
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)C, 2};
   cuuint64_t strides[2] = {(cuuint64_t)Ktot * 2, (cuuint64_t)C * Ktot * 2};
-  cuuint32_t box[3] = {(cuuint32_t)bkw, (cuuint32_t)C, 2};
+  cuuint32_t box[3] = {(cuuint32_t)bkw, (cuuint32_t)C, (cuuint32_t)planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(bkw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -577,12 +645,25 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   p.r_in = p.nbox * p.rb;
   p.r_out = K::ROWS - (p.k2 - 1);
   FD_REQUIRE(p.r_in <= K::RIN_MAX && p.rb <= 256, "fd_respair_fwd: input tile of %d rows exceeds the shared-memory tile", p.r_in);
+  {
+    const char* e = getenv("FD_RP_FIXED_TILE");   // experiment knob: 1 = reserve RIN_MAX rows whatever the halo
+    p.in_alloc_rows = (e && e[0] == '1') ? K::RIN_MAX : p.r_in;
+    // a stage of the ring holds 2 x GROUP weight units (32 KB) when at least two such stages fit: the per-stage
+    // handshake (barrier wait, fences, commit) of the single issuing thread is what the MMAs of a 16 KB stage cannot hide
+    const char* gm = getenv("FD_RP_GROUP_MULT");
+    const int mult = gm ? atoi(gm) : 2;
+    p.group = K::GROUP;
+    if (mult >= 2 && K::stages_for(p.in_alloc_rows, mult * K::GROUP) >= 2) p.group = mult * K::GROUP;
+    p.nstages = K::stages_for(p.in_alloc_rows, p.group);
+    const char* m = getenv("FD_RP_MAX_STAGES");
+    if (m && atoi(m) >= 2 && atoi(m) < p.nstages) p.nstages = atoi(m);
+  }
   CUtensorMap tin, tw1, tw2, tout, tout_last;
   int rc = make_planes_map(&tin, d.in_planes, p.B, p.T, C, K::BK_A, p.rb, 1);
   if (rc) return rc;
-  rc = make_wpair_map(&tw1, d.w1, C, p.k1 * C, K::BKW);
+  rc = make_wpair_map(&tw1, d.w1, C, p.k1 * C, K::BKW, K::MCAST ? 1 : 2);
   if (rc) return rc;
-  rc = make_wpair_map(&tw2, d.w2, C, p.k2 * C, K::BKW);
+  rc = make_wpair_map(&tw2, d.w2, C, p.k2 * C, K::BKW, K::MCAST ? 1 : 2);
   if (rc) return rc;
   rc = make_planes_map(&tout, d.out_planes, p.B, p.T, C, K::BK_A, 128, 1);
   if (rc) return rc;
@@ -597,8 +678,22 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   }
   const int tiles = p.B * ((p.T + p.r_out - 1) / p.r_out);
   const int sms = fd_device_sms(dev);
+  int grid = tiles < sms ? tiles : sms;
   fd_prof_begin(C == 128 ? 8 : C == 64 ? 9 : C == 32 ? 10 : 11, stream);
-  kern<<<tiles < sms ? tiles : sms, K::THREADS, K::SMEM_BYTES, stream>>>(tin, tw1, tw2, tout, tout_last, p);
+  if (K::MCAST) {
+    grid = (grid + 1) / 2 * 2;           // whole pairs; a CTA without tiles only keeps the shared weight ring turning
+    if (grid > sms) grid -= 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = K::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tin, tw1, tw2, tout, tout_last, p));
+  } else {
+    kern<<<grid, K::THREADS, K::SMEM_BYTES, stream>>>(tin, tw1, tw2, tout, tout_last, p);
+  }
   fd_prof_end(stream);
   FD_CHECK_CUDA(cudaGetLastError());
   fd_count_launch(1);
