@@ -2,18 +2,20 @@
 built from the same tap-GEMM kernels (reference: autograd through fish_diffusion/modules/wavenet.py:106-120,194-236
 inside GaussianDiffusion.p_losses, diffusion.py:129-151).
 
-Per residual block the backward is 5 GEMM launches (2x the forward FLOPs):
+Per residual block the backward is 5 GEMM launches (2x the forward FLOPs), issued by ONE native call
+(fd_wavenet_block_bwd) on the tensor-core path:
   dz      = [dx_next/sqrt2 | d_skip] . W2                        data gradient of the output projection (K = 2C)
   dW2     = [dx_next/sqrt2 ; d_skip]^T . z                       weight gradient (K = time)
   dW1     = dy^T . [x(t-d)+d ; x(t)+d ; x(t+d)+d ; cond]         weight gradient of conv taps + conditioner, one GEMM
   dx      = sum_tap dy(t -/+ d) . W1_tap + dx_next/sqrt2         data gradient of the dilated conv (K = 6C)
   dcond  += dy . Wc
-Weight gradients run on folded transposes [channels][B][Tp] (fd_fold_transpose) so that time is the contraction axis of
-the same K-major tensor-core kernel; the tap shift is baked into the transpose (a TMA box must start on a 16-byte
-boundary) and the zero padding of the conv is the zero padding between items.  The operands of one weight-gradient
-GEMM are stacked row-wise so the result lands directly in the packed weight layout.  The tiny step-embedding MLP /
-diffusion projections stay under torch autograd (they act on [B or 1, C] vectors); their output d enters the block
-through the gate-bias tables and its gradient is a column sum of dx.
+Weight gradients read both operands straight from the channels-last planes (MN-major tensor-core operands, fd_wgrad_cl);
+the step vector d_l added to x inside the conv is a rank-one term added afterwards (_add_step_vector_term).  With
+`net.grad_sync` set (train.GradSync) every finished bucket of layers is handed to an NCCL all-reduce from inside the
+loop, overlapping the backward of the layers below.  A K-major path on folded transposes (fd_fold_transpose) remains
+for the SIMT back end and channel counts that are not multiples of 64.  The tiny step-embedding MLP / diffusion
+projections stay under torch autograd (they act on [B or 1, C] vectors); their output d enters the block through the
+gate-bias tables and its gradient is a column sum of dx.
 """
 from __future__ import annotations
 
@@ -279,6 +281,7 @@ class WaveNetTrainFn(torch.autograd.Function):
             gb2_all = torch.cat([cs_x[1:].sum(1) * inv_sqrt2, cs_skip.sum(0).expand(L, C)], dim=1)   # [L,2C]
             for l in range(L):
                 grads[f"l{l}.b2"] = gb2_all[l]
+        # ---- K-major fold path (SIMT back end, channel counts that are not multiples of 64): conv by conv
         for l in (reversed(range(L)) if not direct else ()):
             dil = pk["dil"][l]
             if dx_next is None:     # K offset C selects the skip half of W2^T (aligned: C % 8 == 0)
@@ -291,36 +294,19 @@ class WaveNetTrainFn(torch.autograd.Function):
             N.check(lib.fd_gate_bwd(N.ptr(dz), N.ptr(sv["ys"][l]), N.ptr(dy), rows, C, gate_tile, prec, st), "fd_gate_bwd")
             gb2 = torch.cat([cs_next.sum(0) * inv_sqrt2 if cs_next is not None else torch.zeros(C, **f32),
                              cs_skip.sum(0)])
-            if direct:
-                # ---- rows [dx_next | d_skip] x z (the 1/sqrt2 of the residual rows is applied to all layers at the end)
-                if dx_next is not None:
-                    wgrad_direct([dx_next, dskip_planes], [(0, 0, C), (1, 0, C)], [sv["zs"][l]], [(0, 0, 0, C)],
-                                 out=gw2_all[l])
-                else:
-                    gw2_all[l, :C] = 0
-                    wgrad_direct([dskip_planes], [(0, 0, C)], [sv["zs"][l]], [(0, 0, 0, C)], out=gw2_all[l, C:])
-                grads[f"l{l}.b2"] = gb2
-                # ---- dy x [x(t-d) | x(t) | x(t+d) | cond]: taps are TMA row shifts of the same x planes; the step
-                #      vector d_l added to x inside the conv is a rank-one term, added for all layers after the loop
-                wgrad_direct([dy], [(0, 0, 2 * C)], [sv["xs"][l], sv["cond_planes"]],
-                             [(0, -dil, 0, C), (0, 0, 0, C), (0, dil, 0, C), (1, 0, 0, E)], out=gw1_all[l])
-                N.check(lib.fd_colsum(N.ptr(dy), None, N.ptr(cs_dy[l]), B, T, 2 * C, inv_S, prec, st), "fd_colsum")
-                N.check(lib.fd_colsum_edges(N.ptr(dy), N.ptr(cs_edge[l]), B, T, 2 * C, min(dil, T), inv_S, prec, st),
-                        "fd_colsum_edges")
-            else:
-                # ---- weight gradient of the output projection: rows [residual | skip] x z
-                fold(sv["ys"][l], C, dst=zT, mode=1)
-                if dx_next is not None:
-                    fold(dx_next, C, dst=do_stack, row0=0, scale=inv_sqrt2)
-                grads[f"l{l}.w2"], grads[f"l{l}.b2"] = wgrad(do_stack, 2 * C, zT, C), gb2
-                # ---- weight gradient of the dilated conv taps + conditioner projection in one GEMM (packed layout)
-                fold(dy, 2 * C, dst=dyT)
-                addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
-                for j, sh in enumerate((-dil, 0, dil)):
-                    fold(sv["xs"][l], C, dst=xc_stack, row0=j * C, addvec=addvec, add_bstride=C if Bs > 1 else 0,
-                         pad=PAD - sh)
-                gw1_all[l] = wgrad(dyT, 2 * C, xc_stack, KT)
-                gb1_all[l] = colsum(planes=dy, Nn=2 * C).sum(0)
+            # ---- weight gradient of the output projection: rows [residual | skip] x z
+            fold(sv["ys"][l], C, dst=zT, mode=1)
+            if dx_next is not None:
+                fold(dx_next, C, dst=do_stack, row0=0, scale=inv_sqrt2)
+            grads[f"l{l}.w2"], grads[f"l{l}.b2"] = wgrad(do_stack, 2 * C, zT, C), gb2
+            # ---- weight gradient of the dilated conv taps + conditioner projection in one GEMM (packed layout)
+            fold(dy, 2 * C, dst=dyT)
+            addvec = sv["d"][:, l, :].contiguous()                                   # [Bs, C]
+            for j, sh in enumerate((-dil, 0, dil)):
+                fold(sv["xs"][l], C, dst=xc_stack, row0=j * C, addvec=addvec, add_bstride=C if Bs > 1 else 0,
+                     pad=PAD - sh)
+            gw1_all[l] = wgrad(dyT, 2 * C, xc_stack, KT)
+            gb1_all[l] = colsum(planes=dy, Nn=2 * C).sum(0)
             # ---- data gradients: dx_l = conv^T(dy) + dx_next/sqrt2 ;  dcond += dy . Wc
             dx_l = dx_bufs[l & 1]
             dgrad(dy, 2 * C, bw["w1t"][l], bw["w1t_inv"][l], C, 6 * C,
