@@ -50,6 +50,8 @@ class GemmDesc(ctypes.Structure):
         ("w_inv_scale", c_float), ("res_scale", c_float), ("post_scale", c_float), ("planes_scale", c_float),
         ("act_slope", c_float), ("out_accum", c_int), ("act", c_int), ("prec", c_int), ("backend", c_int),
         ("bias_bstride", c_int),
+        ("gate_y", c_void_p), ("gate_cs", c_void_p), ("gate_cs_edge", c_void_p), ("gate_cs_scale", c_float),
+        ("gate_tile", c_int), ("gate_dil", c_int),
     ]
 
 
@@ -336,7 +338,8 @@ def mrf_finish(ins, out, *, in_slope=0.1, scale=1.0, out_slope=0.1, prec=PREC_F1
 
 
 PROF_KINDS = {0: "linear/tc", 1: "linear/simt", 2: "gate/tc", 3: "gate/simt", 4: "res_skip/tc", 5: "res_skip/simt",
-              6: "mag/tc", 7: "mag/simt", 8: "respair/128", 9: "respair/64", 10: "respair/32", 11: "respair/16"}
+              6: "mag/tc", 7: "mag/simt", 8: "gate_bwd/tc", 12: "respair/128", 13: "respair/64", 14: "respair/32",
+              15: "respair/16"}
 
 
 _prof_on = False
@@ -356,13 +359,13 @@ def prof_is_on() -> bool:
 
 def prof_collect():
     """-> {kind name: (total ms, launches)} of every tap-GEMM launch since prof_enable(True)."""
-    n = len(PROF_KINDS)
+    n = max(PROF_KINDS) + 1
     ms = (ctypes.c_double * n)()
     cnt = (c_longlong * n)()
     rc = lib().fd_prof_collect(ms, cnt, n)
     if rc < 0:
         raise NativeError(f"fd_prof_collect failed: {last_error()}")
-    return {PROF_KINDS[k]: (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}, bool(rc)
+    return {PROF_KINDS.get(k, f"kind{k}"): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}, bool(rc)
 
 
 def tc_supported_linear(n_total: int, k_seg: int, num_seg: int) -> bool:

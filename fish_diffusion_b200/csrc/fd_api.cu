@@ -331,10 +331,20 @@ int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream) {
   p.w = d->w; p.acc_scale = d->w_inv_scale; p.w_kshift = d->w_kshift; p.w_bstride_k = d->w_bstride_k;
   p.epi = FD_EPI_LINEAR;
   p.bias = d->bias; p.bias_bstride = d->bias_bstride;
+  if (d->gate_y != nullptr) {
+    FD_REQUIRE(d->backend == FD_BACKEND_TC, "fd_gemm_cl_fwd: the fused gate backward runs on the tensor-core back end only");
+    FD_REQUIRE(d->out_planes != nullptr && d->gate_tile > 0 && d->n_total % 4 == 0 && (d->gate_tile / 2) % 4 == 0,
+               "fd_gemm_cl_fwd: gate backward needs out_planes and a gate tile");
+  }
   p.addend = d->addend; p.res_f32 = d->res_f32; p.res_planes = d->res_planes; p.res_scale = d->res_scale;
   p.post_scale = d->post_scale; p.out_f32 = d->out_f32; p.out_accum = d->out_accum;
   p.out_planes = d->out_planes; p.planes_scale = d->planes_scale; p.act = d->act; p.act_slope = d->act_slope;
   p.row_mask = d->row_mask;
+  if (d->gate_y != nullptr) {
+    p.epi = FD_EPI_GATE_BWD;
+    p.y_planes = const_cast<uint16_t*>(d->gate_y); p.gate_tile = d->gate_tile; p.dil = d->gate_dil; p.C = d->n_total;
+    p.cs = d->gate_cs; p.cs_edge = d->gate_cs_edge; p.cs_scale = d->gate_cs_scale;
+  }
   return run(p, d->backend, (cudaStream_t)stream);
 }
 

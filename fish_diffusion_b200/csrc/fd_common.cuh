@@ -25,6 +25,7 @@
 #define FD_EPI_GATE 1
 #define FD_EPI_RES_SKIP 2
 #define FD_EPI_MAG 3
+#define FD_EPI_GATE_BWD 4
 
 // activation kinds (linear epilogue)
 #define FD_ACT_NONE 0
@@ -106,6 +107,16 @@ struct FdTapGemm {
   float skip_scale;
   int first_layer, last_layer;
   int C;                    // residual channels
+
+  // ---- FD_EPI_GATE_BWD (training): the accumulator is dz[b,t,c] (n_total = C columns); with the saved pre-activations
+  //      y_planes [2][B][T][2C] (packed order, see FD_EPI_GATE) the epilogue writes the gradient of z = sigmoid(g) tanh(f)
+  //      dy = (dz tanh(f) sg (1-sg) | dz sg (1-tanh(f)^2))  -> out_planes [2][B][T][2C] (packed order)
+  //      and accumulates its column sums: cs[b][col] += cs_scale * sum_t dy,  cs_edge[0/1][b][col] += the same over the
+  //      first / last `dil` steps of the item (bias gradient and rank-one step-vector term of dW1).  cs buffers are zeroed
+  //      by the caller.
+  float* cs;                // [B][2C] or null
+  float* cs_edge;           // [2][B][2C] or null
+  float cs_scale;
 };
 
 // ------------------------------------------------------------------------------------------------

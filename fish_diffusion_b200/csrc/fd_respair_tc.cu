@@ -679,7 +679,7 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   const int tiles = p.B * ((p.T + p.r_out - 1) / p.r_out);
   const int sms = fd_device_sms(dev);
   int grid = tiles < sms ? tiles : sms;
-  fd_prof_begin(C == 128 ? 8 : C == 64 ? 9 : C == 32 ? 10 : 11, stream);
+  fd_prof_begin(C == 128 ? 12 : C == 64 ? 13 : C == 32 ? 14 : 15, stream);
   if (K::MCAST) {
     grid = (grid + 1) / 2 * 2;           // whole pairs; a CTA without tiles only keeps the shared weight ring turning
     if (grid > sms) grid -= 2;

@@ -58,7 +58,7 @@ struct Cfg {
   static constexpr uint32_t SBO = 8 * SWIZZLE_BYTES;
   static constexpr int BIAS_FLOATS = (EPI == FD_EPI_GATE ? 3 : 1) * BLOCK_N * EPI_GROUPS;
   // coalescing epilogue (LINEAR / RES_SKIP with >= 32 columns per warp): a 32x32 fp32 transpose scratch per warp
-  static constexpr bool COALESCED = (EPI == FD_EPI_LINEAR || EPI == FD_EPI_RES_SKIP) && BLOCK_N >= 64;
+  static constexpr bool COALESCED = (EPI == FD_EPI_LINEAR || EPI == FD_EPI_RES_SKIP || EPI == FD_EPI_GATE_BWD) && BLOCK_N >= 64;
   static constexpr int SCRATCH_BYTES = COALESCED ? (EPI_THREADS / 32) * 4096 : 0;
   static constexpr int FIXED_BYTES = 1024 /*align slack*/ + BIAS_FLOATS * 4 + (2 * 8 + 2 * ACC_STAGES) * 8 + 16 + SCRATCH_BYTES;
   static constexpr int RAW_STAGES = (227 * 1024 - 512 - FIXED_BYTES) / STAGE_BYTES;
@@ -222,7 +222,7 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
       // takes a dependent global load and two barriers out of every tile's latency chain
       const long long bias_key = EPI == FD_EPI_GATE ? (long long)b * p.gbias_bstride + n0
                                                     : (long long)b * p.bias_bstride + n0;
-      if (EPI != FD_EPI_MAG && bias_key != staged_key) {
+      if (EPI != FD_EPI_MAG && EPI != FD_EPI_GATE_BWD && bias_key != staged_key) {
         staged_key = bias_key;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(GTHREADS) : "memory");
         if (EPI == FD_EPI_GATE) {
@@ -284,13 +284,116 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
           const int col = half * PER + c + j4;           // first of this lane's 4 columns inside the tile
           const int n = n0 + col;                        // global packed column
           float v[32];
-          constexpr bool LATE_TMEM_LD = EPI == FD_EPI_LINEAR;   // see the LINEAR branch below
+          constexpr bool LATE_TMEM_LD = EPI == FD_EPI_LINEAR || EPI == FD_EPI_GATE_BWD;   // see the LINEAR branch below
           if (!LATE_TMEM_LD) {
             tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
             tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
           }
-          const float4 bias4 = lds128(bias_addr + 4u * col);
-          if (EPI == FD_EPI_RES_SKIP) {
+          const float4 bias4 = EPI == FD_EPI_GATE_BWD ? make_float4(0.f, 0.f, 0.f, 0.f) : lds128(bias_addr + 4u * col);
+          if (EPI == FD_EPI_GATE_BWD) {
+            // backward of z = sigmoid(g) tanh(f) fused into the dz GEMM (training): this lane's 4 channels n..n+3 of 8 rows
+            const int half_g = p.gate_tile / 2;
+            const uint32_t pg = (uint32_t)((n / half_g) * p.gate_tile + (n % half_g));     // packed gate column
+            const uint32_t rowbase = (uint32_t)b * (uint32_t)p.T;
+            const int nrows = rbase < p.T ? min(8, (p.T - rbase + 3) / 4) : 0;
+            const uint32_t W2 = 2u * (uint32_t)p.C;
+            const size_t yplane = (size_t)p.B * p.T * W2;
+            const uint16_t* const y_lo = p.y_planes + yplane;
+            uint16_t* const o_lo = p.out_planes + yplane;
+            tmem_ld16_nowait(taddr + half * PER + c, *reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_ld16_nowait(taddr + half * PER + c + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_wait16(*reinterpret_cast<float(*)[16]>(&v[16]));
+            float4 a[8];
+            warp_transpose_32x32(my_scratch, lane, v, a);
+            float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sf4[4] = {0.f, 0.f, 0.f, 0.f};          // column sums over this lane's rows
+            float e0g[4] = {0.f, 0.f, 0.f, 0.f}, e0f[4] = {0.f, 0.f, 0.f, 0.f}, e1g[4] = {0.f, 0.f, 0.f, 0.f}, e1f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {           // two batches of 4 rows: 16 plane words in flight per batch
+              uint2 gh[4], gl[4], fh[4], fl[4];
+              uint32_t eo4[4];
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const int pp = hb * 4 + q4;
+                eo4[q4] = (rowbase + (uint32_t)min(rbase + pp * 4, p.T - 1)) * W2 + pg;
+                gh[q4] = *reinterpret_cast<const uint2*>(p.y_planes + eo4[q4]);
+                gl[q4] = *reinterpret_cast<const uint2*>(y_lo + eo4[q4]);
+                fh[q4] = *reinterpret_cast<const uint2*>(p.y_planes + eo4[q4] + half_g);
+                fl[q4] = *reinterpret_cast<const uint2*>(y_lo + eo4[q4] + half_g);
+              }
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const int pp = hb * 4 + q4;
+                if (pp >= nrows) break;
+                float g[4], f[4];
+                fd_combine2(gh[q4].x, gl[q4].x, PREC, g[0], g[1]);
+                fd_combine2(gh[q4].y, gl[q4].y, PREC, g[2], g[3]);
+                fd_combine2(fh[q4].x, fl[q4].x, PREC, f[0], f[1]);
+                fd_combine2(fh[q4].y, fl[q4].y, PREC, f[2], f[3]);
+                const float dzv[4] = {a[pp].x * p.acc_scale, a[pp].y * p.acc_scale, a[pp].z * p.acc_scale, a[pp].w * p.acc_scale};
+                float dg[4], df[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float sg = fd_sigmoid(g[i]), th = fd_tanh(f[i]);
+                  dg[i] = dzv[i] * th * sg * (1.f - sg);
+                  df[i] = dzv[i] * sg * (1.f - th * th);
+                }
+                uint32_t h0, l0, h1, l1;
+                fd_split2(dg[0], dg[1], PREC, h0, l0);
+                fd_split2(dg[2], dg[3], PREC, h1, l1);
+                *reinterpret_cast<uint2*>(p.out_planes + eo4[q4]) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(o_lo + eo4[q4]) = make_uint2(l0, l1);
+                fd_split2(df[0], df[1], PREC, h0, l0);
+                fd_split2(df[2], df[3], PREC, h1, l1);
+                *reinterpret_cast<uint2*>(p.out_planes + eo4[q4] + half_g) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(o_lo + eo4[q4] + half_g) = make_uint2(l0, l1);
+                if (p.cs != nullptr) {
+                  const int tt = rbase + pp * 4;
+                  const bool in0 = tt < p.dil, in1 = tt + p.dil >= p.T;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    sg4[i] += dg[i]; sf4[i] += df[i];
+                    if (in0) { e0g[i] += dg[i]; e0f[i] += df[i]; }
+                    if (in1) { e1g[i] += dg[i]; e1f[i] += df[i]; }
+                  }
+                }
+              }
+            }
+            if (p.cs != nullptr) {
+              // rows of the 4 lanes that share these columns (lane bits 3,4), then one atomic per column and warp
+              const bool edge0 = t0 + q * 32 < p.dil, edge1 = t0 + q * 32 + 32 + p.dil > p.T;     // warp-uniform
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                sg4[i] += __shfl_xor_sync(0xffffffffu, sg4[i], 8); sg4[i] += __shfl_xor_sync(0xffffffffu, sg4[i], 16);
+                sf4[i] += __shfl_xor_sync(0xffffffffu, sf4[i], 8); sf4[i] += __shfl_xor_sync(0xffffffffu, sf4[i], 16);
+                if (edge0) {
+                  e0g[i] += __shfl_xor_sync(0xffffffffu, e0g[i], 8); e0g[i] += __shfl_xor_sync(0xffffffffu, e0g[i], 16);
+                  e0f[i] += __shfl_xor_sync(0xffffffffu, e0f[i], 8); e0f[i] += __shfl_xor_sync(0xffffffffu, e0f[i], 16);
+                }
+                if (edge1) {
+                  e1g[i] += __shfl_xor_sync(0xffffffffu, e1g[i], 8); e1g[i] += __shfl_xor_sync(0xffffffffu, e1g[i], 16);
+                  e1f[i] += __shfl_xor_sync(0xffffffffu, e1f[i], 8); e1f[i] += __shfl_xor_sync(0xffffffffu, e1f[i], 16);
+                }
+              }
+              if (rsub == 0) {
+                float* const csb = p.cs + (size_t)b * W2 + pg;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  atomicAdd(csb + i, sg4[i] * p.cs_scale);
+                  atomicAdd(csb + half_g + i, sf4[i] * p.cs_scale);
+                }
+                if (p.cs_edge != nullptr && (edge0 || edge1)) {
+                  float* const ce0 = p.cs_edge + (size_t)b * W2 + pg;
+                  float* const ce1 = ce0 + (size_t)p.B * W2;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (edge0) { atomicAdd(ce0 + i, e0g[i] * p.cs_scale); atomicAdd(ce0 + half_g + i, e0f[i] * p.cs_scale); }
+                    if (edge1) { atomicAdd(ce1 + i, e1g[i] * p.cs_scale); atomicAdd(ce1 + half_g + i, e1f[i] * p.cs_scale); }
+                  }
+                }
+              }
+            }
+          } else if (EPI == FD_EPI_RES_SKIP) {
             // residual columns: x' = (x + y)/sqrt2 on the split planes; skip columns: fp32 accumulation.  32-bit element
             // offsets (checked on the host), rows past T clamped for the loads and skipped for the stores.
             const bool is_res = n0 < p.C;
@@ -582,6 +685,7 @@ int launch_epi(const FdTapGemm& p, cudaStream_t stream) {
   if (p.epi == FD_EPI_GATE) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_GATE>(p, stream);
   if (p.epi == FD_EPI_MAG) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_MAG>(p, stream);
   if (p.epi == FD_EPI_RES_SKIP) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_RES_SKIP>(p, stream);
+  if (p.epi == FD_EPI_GATE_BWD) return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_GATE_BWD>(p, stream);
   return launch_cfg<BLOCK_N, BLOCK_K, FD_EPI_LINEAR>(p, stream);
 }
 
@@ -611,7 +715,7 @@ void pick_cfg(const FdTapGemm& p, int* bn, int* bk) {
     if (n < 64) return;
     *bn = n; *bk = 64;
   } else if (k == 32) {
-    if (p.epi != FD_EPI_LINEAR || n < 32) return;
+    if (p.epi != FD_EPI_LINEAR || n < 32) return;   // (GATE_BWD: BLOCK_K 64 only)
     *bn = n > 64 ? 64 : n; *bk = 32;
   } else {
     if (p.epi != FD_EPI_LINEAR) return;
@@ -643,6 +747,7 @@ int fd_tapgemm_tc_launch(const FdTapGemm& p, cudaStream_t stream) {
   if (bk == 64) {
     if (bn == 256) return launch_epi<256, 64>(p, stream);
     if (bn == 128) return launch_epi<128, 64>(p, stream);
+    if (p.epi == FD_EPI_GATE_BWD) return launch_cfg<64, 64, FD_EPI_GATE_BWD>(p, stream);
     if (p.epi == FD_EPI_RES_SKIP) return launch_cfg<64, 64, FD_EPI_RES_SKIP>(p, stream);
     return launch_cfg<64, 64, FD_EPI_LINEAR>(p, stream);
   }

@@ -241,13 +241,16 @@ int fd_wavenet_block_bwd(const fd_wavenet_bwd_desc* d, void* stream) {
   const float inv_sqrt2 = 0.70710678118654752440f;
   const long long rows = (long long)B * T;
   int rc;
-  // ---- dz = [dx_next | d_skip] . W2 (K offset C selects the skip half when there is no residual gradient)
+  // ---- dy = gate backward of dz = [dx_next | d_skip] . W2, fused into the GEMM's epilogue together with the column
+  //      sums of dy (K offset C selects the skip half of W2^T when there is no residual gradient)
   {
     fd_gemm_desc g;
     memset(&g, 0, sizeof(g));
     g.w = d->w2t; g.n_total = C; g.k_total = 2 * C; g.B = B; g.T = T;
     g.w_inv_scale = d->w2t_inv; g.res_scale = 1.f; g.post_scale = 1.f; g.planes_scale = 1.f;
-    g.out_f32 = d->dz; g.prec = d->prec; g.backend = d->backend;
+    g.out_planes = d->dy; g.prec = d->prec; g.backend = d->backend;
+    g.gate_y = d->y_planes; g.gate_tile = d->gate_tile; g.gate_dil = dil < T ? dil : T;
+    g.gate_cs = d->cs_dy; g.gate_cs_edge = d->cs_edge; g.gate_cs_scale = d->inv_S;
     if (d->dx_next == nullptr) {
       g.src[0] = d->dskip; g.src_C[0] = C; g.num_seg = 1; g.w_kshift = C;
       g.seg_src[0] = 0; g.seg_shift[0] = 0; g.seg_coff[0] = 0; g.seg_klen[0] = C;
@@ -258,8 +261,6 @@ int fd_wavenet_block_bwd(const fd_wavenet_bwd_desc* d, void* stream) {
     rc = fd_gemm_cl_fwd(&g, stream);
     if (rc) return rc;
   }
-  rc = fd_gate_bwd(d->dz, d->y_planes, d->dy, rows, C, d->gate_tile, d->prec & 0xF, stream);
-  if (rc) return rc;
   // ---- gw2 = [dx_next ; d_skip]^T . z
   {
     fd_wgrad_desc w;
@@ -296,10 +297,6 @@ int fd_wavenet_block_bwd(const fd_wavenet_bwd_desc* d, void* stream) {
     rc = fd_reduce_batch(d->part1, d->gw1, d->splits1, (long long)2 * C * (3 * C + E), d->inv_S, stream);
     if (rc) return rc;
   }
-  rc = fd_colsum(d->dy, nullptr, d->cs_dy, B, T, 2 * C, d->inv_S, d->prec & 0xF, stream);
-  if (rc) return rc;
-  rc = fd_colsum_edges(d->dy, d->cs_edge, B, T, 2 * C, dil < T ? dil : T, d->inv_S, d->prec & 0xF, stream);
-  if (rc) return rc;
   // ---- dx_l = conv^T(dy) + dx_next/sqrt2 (mirrored tap shifts, K = 6C)
   {
     fd_gemm_desc g;

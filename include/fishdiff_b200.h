@@ -47,7 +47,7 @@ void fd_set_device(int device);
 long long fd_launch_count(void);
 /* per-launch device timing of the tap-GEMM kernels (CUDA events on the launching stream), used by bench.py for
  * the roofline entry: kind = epilogue*2 + (backend==SIMT); epilogue 0 linear, 1 gate (WaveNet GEMM1),
- * 2 res/skip (WaveNet GEMM2), 3 DFT magnitude; kinds 8..11 = fused ResBlock pair kernel at C = 128/64/32/16.  fd_prof_collect synchronises the device, fills ms_sum[k]/count[k]
+ * 2 res/skip (WaveNet GEMM2), 3 DFT magnitude; kind 8 = gate backward fused into the dz GEMM; kinds 12..15 = fused ResBlock pair kernel at C = 128/64/32/16.  fd_prof_collect synchronises the device, fills ms_sum[k]/count[k]
  * for k < nkinds, resets the log and returns 1 if the log overflowed (65536 launches), 0 otherwise, <0 on error. */
 void fd_prof_enable(int on);
 int fd_prof_collect(double* ms_sum, long long* count, int nkinds);
@@ -284,6 +284,16 @@ typedef struct fd_gemm_desc {
   int out_accum, act, prec, backend;
   int bias_bstride;   /* 0: bias [n_total]; n_total: one bias vector per batch item, bias [B][n_total] (per-utterance
                          speaker / pitch-shift embeddings of DiffSinger.forward_features, diffsinger.py:95-121) */
+  /* gate backward fused into the epilogue (training; tensor-core back end only): when gate_y != NULL the accumulator is
+   * dz [B][T][n_total = C] and the epilogue writes dy = d(sigmoid(g) tanh(f)) (wavenet.py:113-115) for the saved
+   * pre-activations gate_y [2][B][T][2C] (packed order of fd_wavenet_block_fwd_train) into out_planes [2][B][T][2C], and
+   * adds gate_cs_scale * column sums of dy into gate_cs [B][2C] and -- over the first / last gate_dil steps of each item --
+   * gate_cs_edge [2][B][2C] (both zeroed by the caller; may be NULL).  Replaces fd_gate_bwd + fd_colsum + fd_colsum_edges. */
+  const uint16_t* gate_y;
+  float* gate_cs;
+  float* gate_cs_edge;
+  float gate_cs_scale;
+  int gate_tile, gate_dil;
 } fd_gemm_desc;
 int fd_gemm_cl_fwd(const fd_gemm_desc* d, void* stream);
 
