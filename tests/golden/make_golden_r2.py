@@ -10,6 +10,7 @@ and the recorded-random machinery).  Run in the build container:  python tests/g
                      gradients w.r.t. x, the conditioner and every parameter (WN_TC width; norm + samples).
   r2_voc.npz         Generator(config_v1.json) and Generator(config_v1_256.json) at B=1, T=128 (config #3's training
                      segment); SineGen noise by seed as above.
+  r2_voc_resblock2.npz  a small Generator with `resblock: "2"` (ResBlock2, models.py:119-158).
   r2_audio.npz       utils/audio.py get_mel_transform / get_mel_from_audio / dynamic_range_compression (torchaudio
                      MelSpectrogram variant used by the training losses); librosa / fish_audio_preprocess are stubbed,
                      the executed code path touches neither.
@@ -158,6 +159,31 @@ def gold_voc(ref, out):
         out[f"voc_{name}_mel"], out[f"voc_{name}_f0"], out[f"voc_{name}_wav"] = mel, f0, wav.numpy()
         out[f"voc_{name}_wseed"], out[f"voc_{name}_rseed"] = np.array(seed), np.array(seed + 200)
         print(f"  voc {name}: wav {tuple(wav.shape)} rms {float(wav.pow(2).mean().sqrt()):.4f}")
+
+
+def gold_voc_resblock2(ref, out):
+    """Generator with `resblock: "2"` (ResBlock2, models.py:119-158: two dilated convs, one conv per residual) -- the variant
+    the shipped JSON configs do not use."""
+    hd = dict(mg.VOC_SMALL, resblock="2", resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]])
+    h = ref.nsf.AttrDict(hd)
+    torch.manual_seed(141)
+    gen = ref.nsf.Generator(h)
+    gen.remove_weight_norm()
+    with torch.no_grad():
+        for p in gen.parameters():
+            p.mul_(3.0)
+    gen.eval()
+    for k, v in gen.state_dict().items():
+        out["rb2_sd_" + k] = v.numpy()
+    rng = np.random.RandomState(142)
+    B, T = 2, 20
+    mel = (rng.randn(B, h.num_mels, T) - 2.5).clip(-11.5, 2).astype(np.float32)
+    f0 = mg.f0_contour(rng, B, T)
+    with mg.RecordedRandom(143) as rr, torch.no_grad():
+        wav = gen(torch.from_numpy(mel), torch.from_numpy(f0))
+    out["rb2_cfg"] = np.array(json.dumps(hd))
+    out["rb2_mel"], out["rb2_f0"], out["rb2_wav"], out["rb2_rseed"] = mel, f0, wav.numpy(), np.array(143)
+    print(f"  resblock2: wav {tuple(wav.shape)} rms {float(wav.pow(2).mean().sqrt()):.4f}")
 
 
 def gold_audio(ref, out):
@@ -320,7 +346,7 @@ def main():
     torch.set_num_threads(8)
     ref = mg.load_reference()
     groups = {"traj": gold_traj, "train_full": gold_train_full, "train_masked": gold_train_masked, "voc": gold_voc,
-              "audio": gold_audio, "ckpt": gold_ckpt, "diffsinger": gold_diffsinger}
+              "audio": gold_audio, "ckpt": gold_ckpt, "diffsinger": gold_diffsinger, "voc_resblock2": gold_voc_resblock2}
     only = sys.argv[1:]
     for name, fn in groups.items():
         if only and name not in only:

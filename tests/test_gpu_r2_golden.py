@@ -269,3 +269,24 @@ def test_diffsinger_fused_conditioner_planes(golden, golden_cfg):
                                 noise_predictor="naive", seed=9)
         mel_b = model.synthesize(**{**kw, "pitches": T_(g["ds_pitches"])}, sampler_interval=100, noise_predictor="naive", seed=9)
     assert rel_l2(mel_b.cpu().numpy(), mel_a.cpu().numpy()) < 1e-5
+
+
+def test_generator_resblock2_vs_reference(golden):
+    """`resblock: "2"` (ResBlock2, models.py:119-158: x = x + conv_d(lrelu(x)) for d in (1, 3)) against the reference."""
+    g = golden("r2_voc_resblock2")
+    h = json.loads(str(g["rb2_cfg"]))
+    sd = {k[len("rb2_sd_"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("rb2_sd_")}
+    mel, f0 = g["rb2_mel"], g["rb2_f0"]
+    B, T = f0.shape
+    rng = np.random.RandomState(int(g["rb2_rseed"]))
+    ri = rng.rand(B, 9).astype(np.float32)
+    nz = rng.randn(B, T * int(np.prod(h["upsample_rates"])), 9).astype(np.float32)
+    for backend in ("auto", "simt"):
+        gen = Generator(h, backend=backend).to(dev())
+        gen.remove_weight_norm()
+        res = gen.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        wav = gen(T_(mel), T_(f0), rand_ini=T_(ri), sine_noise=T_(nz)).cpu().numpy()
+        e = rel_l2(wav, g["rb2_wav"])
+        print(f"generator[resblock 2, {backend}] rel-L2 vs the reference {e:.2e}")
+        assert wav.shape == g["rb2_wav"].shape and e < 1e-4
