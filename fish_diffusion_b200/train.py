@@ -39,17 +39,22 @@ class GradSync:
         import torch.distributed as dist
         self.dist, self.group, self.bucket_layers = dist, group, int(bucket_layers)
         self.world = dist.get_world_size(group)
+        # NCCL averages inside the collective; other back ends (gloo in the CPU tests) sum and scale afterwards
+        self.native_avg = dist.get_backend(group) == "nccl"
         self.handles = []
         self.bytes = 0
 
     def reduce_async(self, *tensors):
+        op = self.dist.ReduceOp.AVG if self.native_avg else self.dist.ReduceOp.SUM
         for t in tensors:
-            self.handles.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True))
+            self.handles.append((self.dist.all_reduce(t, op=op, group=self.group, async_op=True), t))
             self.bytes += t.numel() * t.element_size()
 
     def wait(self):
-        for h in self.handles:
+        for h, t in self.handles:
             h.wait()
+            if not self.native_avg:
+                t.div_(self.world)
         self.handles = []
 
 
@@ -108,7 +113,11 @@ class DenoiserTrainer:
         if not rest:
             return
         flat = torch._utils._flatten_dense_tensors(rest)
-        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.AVG)
+        if self.sync.native_avg:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.AVG)
+        else:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+            flat.div_(self.world)
         for g, r in zip(rest, torch._utils._unflatten_dense_tensors(flat, rest)):
             g.copy_(r)
 

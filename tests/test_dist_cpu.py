@@ -44,3 +44,29 @@ def test_two_rank_gloo_shard_and_gather():
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r][0] for r in range(world))
     assert all(ret[r][1] == 2.0 for r in range(world))          # max over ranks
+
+
+def _sync_worker(rank, world, port, ret):
+    """GradSync (the bucketed all-reduce the native backward launches) and DenoiserTrainer._reduce_rest on gloo/CPU."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from fish_diffusion_b200.train import GradSync
+    sync = GradSync(bucket_layers=2)
+    a = torch.full((2, 4, 3), float(rank + 1))
+    b = torch.full((2, 4), 10.0 * (rank + 1))
+    sync.reduce_async(a, b)                      # asynchronous: the caller keeps working, joins later
+    c = torch.full((5,), float(rank))
+    sync.reduce_async(c)
+    sync.wait()
+    ok = bool((a == 1.5).all() and (b == 15.0).all() and (c == 0.5).all()) and not sync.handles and sync.bytes > 0
+    ret[rank] = ok
+    torch.distributed.destroy_process_group()
+
+
+def test_grad_sync_buckets_average_over_ranks_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_sync_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))

@@ -94,3 +94,30 @@ def test_time_folded_conv_weight_equals_the_conv():
     # convs the packer leaves alone
     assert Generator._fold_factor(128, 128, 11, 1) == 1 and Generator._fold_factor(32, 32, 11, 3) == 1
     assert Generator._fold_factor(64, 64, 3, 1) == 1 and Generator._fold_factor(16, 32, 3, 1) == 1
+
+
+def test_folded_pair_pack_equals_the_conv():
+    """Generator._pack_conv_folded_pair: the C=16 stage runs the fused pair kernel on the time-folded view [T/2, 32] as a
+    DILATION-1 conv with K' = 2*max|shift|+1 taps of 32x32 blocks.  Exactness of that rewrite, on CPU with torch convs."""
+    import torch
+    import torch.nn.functional as F
+    from fish_diffusion_b200.nsf_hifigan import fold_conv_weight
+    torch.manual_seed(0)
+    C, T, Fd = 16, 64, 2
+    for k, d in ((3, 1), (3, 5), (7, 3), (11, 1), (11, 5)):
+        w = torch.randn(C, C, k, dtype=torch.float64)
+        x = torch.randn(1, C, T, dtype=torch.float64)
+        y = F.conv1d(x, w, padding=(k - 1) // 2 * d, dilation=d)                      # [1,C,T]
+        wf, srows = fold_conv_weight(w, d, Fd)                                        # [F*C, S*F*C]
+        hmax = max(abs(srows[0]), abs(srows[-1]))
+        Kp = 2 * hmax + 1
+        W = torch.zeros((Fd * C, Kp, Fd * C), dtype=torch.float64)
+        wf3 = wf.reshape(Fd * C, len(srows), Fd * C)
+        for j, sr in enumerate(srows):
+            W[:, sr + hmax, :] = wf3[:, j, :]
+        # folded view: row r holds time steps 2r, 2r+1 -> channels (f, c)
+        xf = x[0].t().reshape(T // Fd, Fd * C).t()[None]                              # [1, F*C, T/F]
+        yf = F.conv1d(xf, W.permute(0, 2, 1).contiguous(), padding=hmax)              # [1, F*C, T/F]
+        back = yf[0].t().reshape(T, C).t()[None]
+        assert torch.allclose(back, y, atol=1e-10), (k, d)
+        assert Kp % 2 == 1 and (Kp - 1) <= 56
