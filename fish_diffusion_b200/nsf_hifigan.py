@@ -434,15 +434,26 @@ class Generator(nn.Module):
                         else:
                             self._conv(rb["c2"][m], PB, B, Lo, res_f32=res, **final_kw)
                 else:
+                    # ResBlock2 (models.py:150-155) with the reference's aliasing: its LeakyReLU is IN PLACE, so the residual
+                    # that is added is lrelu(x) (not x), and the stage input shared by the three blocks (models.py:426-430)
+                    # has been LeakyReLU'd once more for every block that ran before: block j sees u_j = lrelu^(j+1)(x).
+                    # Everything therefore lives in plane tensors: conv input = residual = planes of the lrelu'd value.
                     n = len(rb["c"])
+                    if j == 0:
+                        U = PA                                    # planes of lrelu(x)
+                    else:
+                        U2 = torch.empty_like(PA)                 # one more LeakyReLU on the shared stage input
+                        N.mrf_finish([U], U2, in_slope=1.0, scale=1.0, out_slope=LRELU_SLOPE, prec=pk["prec"])
+                        U = U2
+                    inp = U
                     for m in range(n):
-                        inp = PA if m == 0 else PC
-                        res = X if m == 0 else Xj
                         if m < n - 1:
-                            self._conv(rb["c"][m], inp, B, Lo, res_f32=res, out_f32=Xj, out_planes=PC,
-                                       act=N.ACT_LRELU, act_slope=LRELU_SLOPE)
+                            self._conv(rb["c"][m], inp, B, Lo, res_planes=inp, out_planes=PC, act=N.ACT_LRELU,
+                                       act_slope=LRELU_SLOPE)
+                            inp = PC
+                            PC = torch.empty_like(PC)
                         else:
-                            self._conv(rb["c"][m], inp, B, Lo, res_f32=res, **final_kw)
+                            self._conv(rb["c"][m], inp, B, Lo, res_planes=inp, **final_kw)
             cur, L = nxt, Lo
             del X, PA, XS, PB, PC, Xj
         wav = torch.empty((B, 1, S), **f32)

@@ -118,6 +118,21 @@ def resblock1(sd, prefix, x, k, dilations):
     return x
 
 
+def resblock2_inplace(sd, prefix, x, k, dilations):
+    """ResBlock2.forward (models.py:150-155) INCLUDING its aliasing: `xt = F.leaky_relu(x, LRELU_SLOPE, inplace=True)`
+    rewrites x itself, so (a) the residual added is lrelu(x), not x, and (b) the caller's tensor -- the stage input that
+    Generator.forward hands to all three ResBlocks (models.py:426-430) -- is left LeakyReLU'd once more after every block.
+    Returns (block output, the stage input as the next block will see it)."""
+    x = lrelu(x, LRELU_SLOPE)                 # in place on the shared stage input
+    shared_after = x
+    for m, d in enumerate(dilations):
+        if m > 0:
+            x = lrelu(x, LRELU_SLOPE)         # in place on the block's own intermediate
+        xt = conv1d(x, sd[f"{prefix}convs.{m}.weight"], sd[f"{prefix}convs.{m}.bias"], dilation=d, padding=get_padding(k, d))
+        x = xt + x
+    return x, shared_after
+
+
 def generator_forward(sd, h, mel, f0, rand_ini, noise, mode="exact", dtype=np.float64, return_source=False):
     """Generator.forward (models.py:407-438) with weight norm already folded (plain `weight` keys).
     mel [B,M,T], f0 [B,T]; returns wav [B,1,T*hop]."""
@@ -142,7 +157,10 @@ def generator_forward(sd, h, mel, f0, rand_ini, noise, mode="exact", dtype=np.fl
         x = x + xs_src
         xs = None
         for j, (rk, rd) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
-            y = resblock1(sd, f"resblocks.{i * nk + j}.", x, rk, rd)
+            if str(h.get("resblock", "1")) == "1":
+                y = resblock1(sd, f"resblocks.{i * nk + j}.", x, rk, rd)
+            else:
+                y, x = resblock2_inplace(sd, f"resblocks.{i * nk + j}.", x, rk, rd)
             xs = y if xs is None else xs + y
         x = xs / nk
     x = lrelu(x, 0.01)  # F.leaky_relu default slope (models.py:434)
