@@ -45,6 +45,9 @@
 #ifndef FD_RP_MCAST
 #define FD_RP_MCAST(C) ((C) == 128)
 #endif
+#ifndef FD_RP_MCAST_DEFAULT
+#define FD_RP_MCAST_DEFAULT 1
+#endif
 #ifndef FD_RP_STAGE_MAJOR
 #define FD_RP_STAGE_MAJOR(C) ((C) == 64 || (C) == 32)
 #endif
@@ -189,7 +192,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int C, int PREC>
+template <int C, int PREC, bool MC>
 __global__ void __launch_bounds__((RpCfg<C>::THREADS), 1)
 fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
@@ -225,7 +228,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     prefetch_tmap(&tm_in); prefetch_tmap(&tm_w1); prefetch_tmap(&tm_w2); prefetch_tmap(&tm_out); prefetch_tmap(&tm_out_last);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], K::MCAST ? 2 : 1); }
+    for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], MC ? 2 : 1); }
     mbar_init(in_full, 1); mbar_init(in_empty, K::EPI_WARPS);
     for (int j = 0; j < MB; ++j) {
       mbar_init(&acc1_full[j], 1); mbar_init(&mid_ready[j], K::EPI_WARPS / K::GROUPS); mbar_init(&acc2_full[j], 1);
@@ -245,14 +248,14 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (K::MCAST) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
+  if (MC) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
   // every CTA runs the same number of iterations (the pair shares the weight ring); iterations past the last tile only
   // keep the ring turning
   const int iters = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t crank = K::MCAST ? cluster_ctarank() : 0u;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   const int units1 = p.k1 * K::UNITS_PER_TAP, units2 = p.k2 * K::UNITS_PER_TAP;
 
@@ -273,7 +276,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
               for (int g = 0; g < nb; ++g) {
                 const int u = u0 + g;
                 const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
-                if (K::MCAST)     // this CTA's plane of the unit, into both CTAs
+                if (MC)     // this CTA's plane of the unit, into both CTAs
                   tma_load_3d_mcast(slot + g * K::UNIT_BYTES + crank * (C * K::WROWB), tm, &w_full[stage],
                                     tap * C + kw * K::BKW, 0, (int)crank, (uint16_t)3);
                 else
@@ -322,7 +325,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                                     (K::STAGE_MAJOR ? 1 : MB);
         for (int sidx = 0; sidx < stages_per_tile; ++sidx) {
           mbar_wait(&w_full[stage], phase);
-          if (elect_one()) { if (K::MCAST) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
+          if (elect_one()) { if (MC) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
           __syncwarp();
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -377,7 +380,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
               }
               __syncwarp();
             }
-            if (elect_one()) { if (K::MCAST) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
+            if (elect_one()) { if (MC) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
             __syncwarp();
             if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -424,7 +427,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
               }
               __syncwarp();
             }
-            if (elect_one()) { if (K::MCAST) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
+            if (elect_one()) { if (MC) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
             __syncwarp();
             if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -590,7 +593,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (K::MCAST) cluster_sync_all();      // no multicast write / remote arrive may target a CTA that has exited
+  if (MC) cluster_sync_all();      // no multicast write / remote arrive may target a CTA that has exited
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS)
@@ -635,7 +638,7 @@ int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw
   return 0;
 }
 
-template <int C, int PREC>
+template <int C, int PREC, bool MC>
 int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) {
   using K = RpCfg<C>;
   // tile geometry: MB blocks of 128 rows; the input tile is nbox TMA boxes of rb rows
@@ -661,15 +664,15 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   CUtensorMap tin, tw1, tw2, tout, tout_last;
   int rc = make_planes_map(&tin, d.in_planes, p.B, p.T, C, K::BK_A, p.rb, 1);
   if (rc) return rc;
-  rc = make_wpair_map(&tw1, d.w1, C, p.k1 * C, K::BKW, K::MCAST ? 1 : 2);
+  rc = make_wpair_map(&tw1, d.w1, C, p.k1 * C, K::BKW, MC ? 1 : 2);
   if (rc) return rc;
-  rc = make_wpair_map(&tw2, d.w2, C, p.k2 * C, K::BKW, K::MCAST ? 1 : 2);
+  rc = make_wpair_map(&tw2, d.w2, C, p.k2 * C, K::BKW, MC ? 1 : 2);
   if (rc) return rc;
   rc = make_planes_map(&tout, d.out_planes, p.B, p.T, C, K::BK_A, 128, 1);
   if (rc) return rc;
   rc = make_planes_map(&tout_last, d.out_planes, p.B, p.T, C, K::BK_A, 128 - (p.k2 - 1), 1);
   if (rc) return rc;
-  auto kern = fd_respair_tc_kernel<C, PREC>;
+  auto kern = fd_respair_tc_kernel<C, PREC, MC>;
   static bool attr_set[FD_MAX_DEVICES] = {false};
   const int dev = fd_current_device();
   if (!attr_set[dev]) {
@@ -680,7 +683,7 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   const int sms = fd_device_sms(dev);
   int grid = tiles < sms ? tiles : sms;
   fd_prof_begin(C == 128 ? 12 : C == 64 ? 13 : C == 32 ? 14 : 15, stream);
-  if (K::MCAST) {
+  if (MC) {
     grid = (grid + 1) / 2 * 2;           // whole pairs; a CTA without tiles only keeps the shared weight ring turning
     if (grid > sms) grid -= 2;
     cudaLaunchConfig_t cfg;
@@ -702,7 +705,12 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
 
 template <int C>
 int launch_respair_prec(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t stream) {
-  return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16>(d, p, stream) : launch_respair<C, FD_BF16>(d, p, stream);
+  // FD_RP_MCAST(C) names the widths that have the 2-CTA weight-multicast variant; FD_RP_MCAST_ON=0/1 picks at run time
+  static const int mc_env = [] { const char* e = getenv("FD_RP_MCAST_ON"); return e ? atoi(e) : -1; }();
+  if (RpCfg<C>::MCAST && mc_env != 0 && (mc_env == 1 || FD_RP_MCAST_DEFAULT))
+    return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16, RpCfg<C>::MCAST>(d, p, stream)
+                                    : launch_respair<C, FD_BF16, RpCfg<C>::MCAST>(d, p, stream);
+  return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16, false>(d, p, stream) : launch_respair<C, FD_BF16, false>(d, p, stream);
 }
 
 }  // namespace
