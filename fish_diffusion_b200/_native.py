@@ -13,7 +13,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ub
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfishdiff_b200.so")
+# FISHDIFF_B200_LIB: another build of the same C ABI (A/B runs of two kernel versions on one box); there is no non-CUDA fallback
+LIB_PATH = os.environ.get("FISHDIFF_B200_LIB") or os.path.join(_HERE, "libfishdiff_b200.so")
 
 PREC_F16, PREC_BF16 = 0, 1
 PREC_SINGLE = 0x10   # or-ed into the prec of GEMM calls: one product over the hi planes
@@ -62,7 +63,7 @@ class ResPairDesc(ctypes.Structure):
         ("out_planes", c_void_p),
         ("B", c_int), ("T", c_int), ("C", c_int), ("k1", c_int), ("d1", c_int), ("k2", c_int),
         ("w1_inv_scale", c_float), ("w2_inv_scale", c_float), ("in_slope", c_float), ("out_slope", c_float),
-        ("planes_scale", c_float), ("prec", c_int),
+        ("planes_scale", c_float), ("prec", c_int), ("kmask1", c_ulonglong), ("kmask2", c_ulonglong),
     ]
 
 
@@ -318,8 +319,9 @@ def respair_supported(C: int, k1: int, d1: int, k2: int) -> bool:
 
 
 def respair(in_planes, w1, w2, b1, b2, B, T, C, k1, d1, k2, *, out_planes, w1_inv_scale=1.0, w2_inv_scale=1.0,
-            in_slope=0.1, out_slope=0.1, planes_scale=1.0, prec=PREC_F16):
-    """Fused ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) on planes of lrelu(x) -> planes of lrelu(x') (fd_respair_fwd)."""
+            in_slope=0.1, out_slope=0.1, planes_scale=1.0, prec=PREC_F16, kmask1=0, kmask2=0):
+    """Fused ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) on planes of lrelu(x) -> planes of lrelu(x') (fd_respair_fwd).
+    kmask1 / kmask2: block-sparsity hints (bit tap*(C/16)+s <=> input channels [16s,16s+16) of that tap are non-zero)."""
     d = ResPairDesc()
     d.in_planes, d.w1, d.w2, d.b1, d.b2 = ptr(in_planes), ptr(w1), ptr(w2), ptr(b1), ptr(b2)
     d.out_planes = ptr(out_planes)
@@ -327,6 +329,7 @@ def respair(in_planes, w1, w2, b1, b2, B, T, C, k1, d1, k2, *, out_planes, w1_in
     d.w1_inv_scale, d.w2_inv_scale = w1_inv_scale, w2_inv_scale
     d.in_slope, d.out_slope, d.planes_scale = in_slope, out_slope, planes_scale
     d.prec = prec
+    d.kmask1, d.kmask2 = int(kmask1), int(kmask2)
     check(lib().fd_respair_fwd(ctypes.byref(d), stream_ptr(in_planes.device)), "fd_respair_fwd")
 
 

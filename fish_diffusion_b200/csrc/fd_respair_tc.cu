@@ -48,6 +48,12 @@
 #ifndef FD_RP_MCAST_DEFAULT
 #define FD_RP_MCAST_DEFAULT 1
 #endif
+#ifndef FD_RP_OCC_DEFAULT
+#define FD_RP_OCC_DEFAULT 2
+#endif
+#ifndef FD_RP_EW_DEFAULT
+#define FD_RP_EW_DEFAULT 16
+#endif
 #ifndef FD_RP_STAGE_MAJOR
 #define FD_RP_STAGE_MAJOR(C) ((C) == 64 || (C) == 32)
 #endif
@@ -68,15 +74,24 @@ struct FdResPairK {
   float in_slope_inv, out_slope, planes_scale;
   const float* b1;
   const float* b2;
+  // weight units (tap, K slice of BKW channels) that hold non-zero weights, in order, and per listed unit one bit per
+  // K16 step (bit i * (BKW/16) + ks): the time-folded C = 16 convs are block-sparse (fd_respair_desc.kmask1/2)
+  int n1, n2, masked1, masked2;
+  unsigned long long km1, km2;
+  unsigned char ul1[64], ul2[64];
 };
 
 // A tile is MB blocks of 128 rows with MB * C = 128: every tile holds the same number of elements whatever the
 // channel count, so the per-tile latency chain (TMA load -> GEMM1 -> epilogue -> GEMM2 -> epilogue -> TMA store) and
 // the (k-1)-row halo are amortised over 1024 rows at C = 16 instead of 128, and the epilogue of block j overlaps the
 // MMAs of block j+1.
-template <int C>
+// OCC = CTAs per SM: 2 halves the tile (MB blocks), the shared memory and the TMEM columns of a CTA, so that the tensor
+// phase of one CTA runs under the epilogue phase of the other (the narrow widths spend most of a tile in the epilogues,
+// and their accumulators fill all 512 TMEM columns at OCC = 1, which rules out double buffering inside one CTA).
+template <int C, int EW = FD_RP_EPI_WARPS(C), int OCC = 1>
 struct RpCfg {
-  static constexpr int MB = 128 / C;
+  static constexpr int MB = 128 / C / OCC;
+  static_assert(MB >= 1, "two CTAs per SM need at least one 128-row block each");
   static constexpr int ROWS = MB * 128;
   static constexpr int BK_A = C >= 64 ? 64 : C;          // channels per shared-memory activation block
   static constexpr int NKB = C / BK_A;
@@ -106,7 +121,7 @@ struct RpCfg {
   // the MMAs of the following blocks.
   static constexpr bool STAGE_MAJOR = FD_RP_STAGE_MAJOR(C);
   static constexpr bool MCAST = FD_RP_MCAST(C);
-  static constexpr int EPI_WARPS = FD_RP_EPI_WARPS(C);
+  static constexpr int EPI_WARPS = EW;
   static constexpr int HALVES_WANT = C >= 128 ? 4 : C >= 32 ? 2 : 1;
   static constexpr int HALVES = HALVES_WANT > EPI_WARPS / 4 ? EPI_WARPS / 4 : HALVES_WANT;   // column split of a block
   static constexpr int GROUPS = EPI_WARPS / 4 / HALVES;     // warp groups taking alternate blocks
@@ -114,11 +129,12 @@ struct RpCfg {
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int GTHREADS = EPI_THREADS / GROUPS;
   static constexpr int THREADS = 128 + EPI_THREADS;
-  static constexpr int TMEM_COLS = 512;                     // acc1[j] at j*2C, acc2[j] at 256 + j*2C
+  static constexpr int ACC2_OFF = MB * 2 * C;               // acc1[j] at j*2C, acc2[j] at ACC2_OFF + j*2C
+  static constexpr int TMEM_COLS = 2 * ACC2_OFF;
   static constexpr int NBAR = 2 + 3 * MB;
   static constexpr int MAX_STAGES = 8;
   static constexpr int HEAD_BYTES = 2048;                   // biases (2C floats <= 1 KB) + barriers, in front of the tiles
-  static constexpr int SMEM_BYTES = 227 * 1024;             // always the whole shared memory: the ring takes what is left
+  static constexpr int SMEM_BYTES = OCC == 2 ? 113 * 1024 : 227 * 1024;   // always the CTA's whole share: the ring takes what is left
   static constexpr int FIXED_MAX = 1024 + HEAD_BYTES + NKB * 2 * IN_PLANE_BYTES_MAX + MID_BYTES;
   static_assert((SMEM_BYTES - FIXED_MAX) / STAGE_BYTES >= 2, "weight ring needs two stages");
   static_assert(2 * C * 4 + (2 * MAX_STAGES + NBAR + 2) * 8 + 16 <= HEAD_BYTES, "head region too small");
@@ -192,12 +208,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int C, int PREC, bool MC>
-__global__ void __launch_bounds__((RpCfg<C>::THREADS), 1)
+template <int C, int PREC, bool MC, int EW, int OCC>
+__global__ void __launch_bounds__((RpCfg<C, EW, OCC>::THREADS), OCC)
 fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
                      const __grid_constant__ CUtensorMap tm_out_last, const FdResPairK p) {
-  using K = RpCfg<C>;
+  using K = RpCfg<C, EW, OCC>;
   constexpr int MB = K::MB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -240,8 +256,8 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                  "r"((uint32_t)K::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // biases; the 16 trailing rows of the mid tile are zero for the whole kernel
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { bias_s[i] = p.b1[i]; bias_s[C + i] = p.b2[i]; }
+  // biases (b2 pre-multiplied by the weight prescale of c2); the 16 trailing rows of the mid tile are zero for the whole kernel
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { bias_s[i] = p.b1[i]; bias_s[C + i] = p.b2[i] * p.s2; }
   for (int i = threadIdx.x; i < K::NKB * 2 * K::ROWB; i += blockDim.x)      // 16 rows = ROWB 16-byte chunks per plane
     *reinterpret_cast<uint4*>(mid_s + (i / K::ROWB) * K::MID_PLANE_BYTES + K::ROWS * K::ROWB + (i % K::ROWB) * 16) =
         make_uint4(0, 0, 0, 0);
@@ -251,13 +267,13 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   if (MC) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + K::ACC2_OFF;
   // every CTA runs the same number of iterations (the pair shares the weight ring); iterations past the last tile only
   // keep the ring turning
   const int iters = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
-  const int units1 = p.k1 * K::UNITS_PER_TAP, units2 = p.k2 * K::UNITS_PER_TAP;
+  const int units1 = p.n1, units2 = p.n2;          // listed (non-zero) weight units of c1 / c2
 
   if (warp == 0) {
     // =========================================================== weight producer (the pair's weights, once per block)
@@ -267,6 +283,8 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         for (int g2 = 0; g2 < 2; ++g2) {
           const CUtensorMap* tm = g2 == 0 ? &tm_w1 : &tm_w2;
           const int units = g2 == 0 ? units1 : units2;
+          const unsigned char* ul = g2 == 0 ? p.ul1 : p.ul2;
+          const bool pmasked = (g2 == 0 ? p.masked1 : p.masked2) != 0;
           for (int j = 0; j < (K::STAGE_MAJOR ? 1 : MB); ++j) {
             for (int u0 = 0; u0 < units; u0 += GROUP) {
               const int nb = min(GROUP, units - u0);
@@ -274,7 +292,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
               mbar_expect_tx(&w_full[stage], nb * K::UNIT_BYTES);
               uint8_t* slot = w_s + stage * STAGE_BYTES_RT;
               for (int g = 0; g < nb; ++g) {
-                const int u = u0 + g;
+                const int u = pmasked ? (int)ul[u0 + g] : u0 + g;
                 const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
                 if (MC)     // this CTA's plane of the unit, into both CTAs
                   tma_load_3d_mcast(slot + g * K::UNIT_BYTES + crank * (C * K::WROWB), tm, &w_full[stage],
@@ -334,6 +352,10 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 #pragma unroll 1
       for (int g2 = 0; g2 < 2; ++g2) {
         const int units = g2 == 0 ? units1 : units2;
+        const unsigned char* ul = g2 == 0 ? p.ul1 : p.ul2;
+        const unsigned long long km = g2 == 0 ? p.km1 : p.km2;
+        const bool masked = (g2 == 0 ? p.masked1 : p.masked2) != 0;
+        constexpr int KS = K::BKW / 16;
         const uint32_t a_base = g2 == 0 ? smem_u32(in_s) : smem_u32(mid_s);
         const uint32_t a_kb = g2 == 0 ? in_kb : K::MID_KB_BYTES;
         const uint32_t a_plane = g2 == 0 ? (uint32_t)in_plane : (uint32_t)K::MID_PLANE_BYTES;
@@ -345,7 +367,8 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             for (int j = 0; j < MB; ++j) mbar_wait(&mid_ready[j], it & 1);
             tc_fence_after();
           }
-          int u = 0;
+          int ui = 0;
+          uint32_t started = g2;                   // GEMM2 accumulates on the residual-initialised accumulator
 #pragma unroll 1
           for (int u0 = 0; u0 < units; u0 += GROUP) {
             const int nb = min(GROUP, units - u0);
@@ -353,12 +376,14 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             tc_fence_after();
             const uint32_t w_stage = smem_u32(w_s + stage * STAGE_BYTES_RT);
 #pragma unroll 1
-            for (int g = 0; g < nb; ++g, ++u) {
+            for (int g = 0; g < nb; ++g, ++ui) {
+              const int u = masked ? (int)ul[ui] : ui;      // dense convs: no table look-up on the issue path
               const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
               const int ch = kw * K::BKW;
               const uint32_t a0 = a_base + (ch / K::BK_A) * a_kb + (uint32_t)tap * tap_bytes + (ch % K::BK_A) * 2;
               const uint64_t dw = DESC_HI_W | (uint64_t)(((w_stage + g * K::UNIT_BYTES) & 0x3FFFF) >> 4);
-              const uint32_t first = (g2 == 1 || u != 0) ? 1u : 0u;
+              const uint32_t kbits = masked ? (uint32_t)(km >> (ui * KS)) & ((1u << KS) - 1u) : ((1u << KS) - 1u);
+              const uint32_t first = started;
               if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < MB; ++j) {
@@ -366,18 +391,21 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                   const uint32_t a_hi = a0 + (uint32_t)(j * 128) * K::ROWB;
                   const uint64_t da_hi = DESC_HI_A | (uint64_t)((a_hi & 0x3FFFF) >> 4);
                   const uint64_t da_lo = DESC_HI_A | (uint64_t)(((a_hi + a_plane) & 0x3FFFF) >> 4);
+                  uint32_t accum = first;
 #pragma unroll
                   for (int k = 0; k < K::BKW / 16; ++k) {
-                    const uint32_t accum = (k != 0) ? 1u : first;
+                    if (!((kbits >> k) & 1u)) continue;             // an all-zero K16 slice of this tap
                     if (!single) {
                       umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_2c, accum);
                       umma_f16(d_tmem, da_lo + 2 * k, dw + 2 * k, idesc_c, 1u);
                     } else {
                       umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_c, accum);
                     }
+                    accum = 1u;
                   }
                 }
               }
+              if (kbits) started = 1u;
               __syncwarp();
             }
             if (elect_one()) { if (MC) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
@@ -396,7 +424,8 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             mbar_wait(&mid_ready[j + 1 < MB ? j + 1 : j], it & 1);
             tc_fence_after();
           }
-          int u = 0;
+          int ui = 0;
+          uint32_t started = g2;
 #pragma unroll 1
           for (int u0 = 0; u0 < units; u0 += GROUP) {
             const int nb = min(GROUP, units - u0);
@@ -404,27 +433,31 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             tc_fence_after();
             const uint32_t w_stage = smem_u32(w_s + stage * STAGE_BYTES_RT);
 #pragma unroll 1
-            for (int g = 0; g < nb; ++g, ++u) {
+            for (int g = 0; g < nb; ++g, ++ui) {
+              const int u = masked ? (int)ul[ui] : ui;      // dense convs: no table look-up on the issue path
               const int tap = u / K::UNITS_PER_TAP, kw = u % K::UNITS_PER_TAP;
               const int ch = kw * K::BKW;
+              const uint32_t kbits = masked ? (uint32_t)(km >> (ui * KS)) & ((1u << KS) - 1u) : ((1u << KS) - 1u);
               const uint32_t a_hi = a_base + (ch / K::BK_A) * a_kb + (uint32_t)(j * 128) * K::ROWB + (uint32_t)tap * tap_bytes +
                                     (ch % K::BK_A) * 2;
               const uint64_t da_hi = DESC_HI_A | (uint64_t)((a_hi & 0x3FFFF) >> 4);
               const uint64_t da_lo = DESC_HI_A | (uint64_t)(((a_hi + a_plane) & 0x3FFFF) >> 4);
               const uint64_t dw = DESC_HI_W | (uint64_t)(((w_stage + g * K::UNIT_BYTES) & 0x3FFFF) >> 4);
-              const uint32_t first = (g2 == 1 || u != 0) ? 1u : 0u;
               if (elect_one()) {
+                uint32_t accum = started;
 #pragma unroll
                 for (int k = 0; k < K::BKW / 16; ++k) {
-                  const uint32_t accum = (k != 0) ? 1u : first;
+                  if (!((kbits >> k) & 1u)) continue;
                   if (!single) {
                     umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_2c, accum);     // a_hi x [w_hi | w_lo] -> [0,2C)
                     umma_f16(d_tmem, da_lo + 2 * k, dw + 2 * k, idesc_c, 1u);         // a_lo x w_hi         -> [0,C)
                   } else {
                     umma_f16(d_tmem, da_hi + 2 * k, dw + 2 * k, idesc_c, accum);
                   }
+                  accum = 1u;
                 }
               }
+              if (kbits) started = 1u;
               __syncwarp();
             }
             if (elect_one()) { if (MC) umma_commit_mcast(&w_empty[stage], 3); else umma_commit(&w_empty[stage]); }
@@ -450,87 +483,96 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t in_u = smem_u32(in_s), mid_u = smem_u32(mid_s);
     const float slope_mid = 0.1f;
+    const float s2_neg = p.s2 * p.in_slope_inv;
+    const float out_c = p.inv_s2 * p.planes_scale, out_cs = out_c * p.out_slope;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / tiles_t, t0 = (tile % tiles_t) * p.r_out;
-      // ---- phase 1 per block: GEMM1 done -> residual into accumulator 2, c1 output into the mid tile
+      // ---- phase 1a: residual + c2 bias -> accumulator 2 (pre-scaled by the weight prescale of c2), zeros in the [w_lo]
+      // half.  Needs only the input tile (and this thread's own reads of accumulator 2 for the previous tile, which are
+      // complete), so it runs while GEMM1 of this tile is still being issued.
+      mbar_wait(in_full, it & 1);                    // visibility of the TMA-written input tile to these threads
+#pragma unroll 1
+      for (int j = grp; j < MB; j += K::GROUPS) {
+        const int n = j * 128 + row + p.h1 + p.h2;
+#pragma unroll
+        for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+          const int col = col_base + c16 * 16;
+          const int kb = col / K::BK_A, cc = col % K::BK_A;
+          const uint32_t base = in_u + kb * in_kb;
+          float v[16];
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const uint32_t off = swz((uint32_t)n * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+            const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + in_plane + off);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float a0, a1;
+              fd_combine2(hw[jj], lw[jj], PREC, a0, a1);
+              // x = p >= 0 ? p : p / slope (the planes hold lrelu(x)); (x + b2) * s2 as one fma
+              v[hq * 8 + 2 * jj] = fmaf(a0, a0 >= 0.f ? p.s2 : s2_neg, bias_s[C + col + hq * 8 + 2 * jj]);
+              v[hq * 8 + 2 * jj + 1] = fmaf(a1, a1 >= 0.f ? p.s2 : s2_neg, bias_s[C + col + hq * 8 + 2 * jj + 1]);
+            }
+          }
+          tmem_st16(acc2 + j * 2 * C + lane_addr + col, v);
+          if (!p.single) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            tmem_st16(acc2 + j * 2 * C + lane_addr + C + col, v);
+          }
+        }
+      }
+      tmem_st_wait();
+      // ---- phase 1b per block: GEMM1 done -> bias, LeakyReLU, zero outside [0,T), split planes -> mid tile (c2's A operand)
 #pragma unroll 1
       for (int j = grp; j < MB; j += K::GROUPS) {
         mbar_wait(&acc1_full[j], it & 1);
         tc_fence_after();
         if (j == grp) {
-          mbar_wait(in_full, it & 1);                  // visibility of the TMA-written input tile to these threads
           // the staging image (= mid tile) of the previous tile must have been read by its TMA stores
           if (issuer) bulk_wait_read0();
           asm volatile("bar.sync 8, %0;" ::"r"(K::EPI_THREADS) : "memory");
         }
         const int m = j * 128 + row;                   // row of the mid tile
-        // (a) residual + c2 bias -> accumulator 2 (pre-scaled by the weight prescale of c2), zeros in the [w_lo] half
-        {
-          const int n = m + p.h1 + p.h2;
+        const int t = t0 - p.h2 + m;
+        const bool ok = t >= 0 && t < p.T;
+        const bool all_ok = __all_sync(0xffffffffu, ok);
 #pragma unroll
-          for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
-            const int col = col_base + c16 * 16;
-            const int kb = col / K::BK_A, cc = col % K::BK_A;
-            const uint32_t base = in_u + kb * in_kb;
-            float v[16];
+        for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
+          const int col = col_base + c16 * 16;
+          float a[16], a2[16];
+          tmem_ld16_nowait(acc1 + j * 2 * C + lane_addr + col, a);
+          if (!p.single) tmem_ld16_nowait(acc1 + j * 2 * C + lane_addr + C + col, a2);
+          tmem_wait16(a);
+          if (!p.single) {
+            tmem_wait16(a2);
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              const uint32_t off = swz((uint32_t)n * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
-              const uint4 h4 = lds_u4(base + off), l4 = lds_u4(base + in_plane + off);
-              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                float a0, a1;
-                fd_combine2(hw[jj], lw[jj], PREC, a0, a1);
-                a0 = a0 >= 0.f ? a0 : a0 * p.in_slope_inv;
-                a1 = a1 >= 0.f ? a1 : a1 * p.in_slope_inv;
-                v[hq * 8 + 2 * jj] = (a0 + bias_s[C + col + hq * 8 + 2 * jj]) * p.s2;
-                v[hq * 8 + 2 * jj + 1] = (a1 + bias_s[C + col + hq * 8 + 2 * jj + 1]) * p.s2;
-              }
-            }
-            tmem_st16(acc2 + j * 2 * C + lane_addr + col, v);
-            if (!p.single) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = 0.f;
-              tmem_st16(acc2 + j * 2 * C + lane_addr + C + col, v);
-            }
+            for (int i = 0; i < 16; ++i) a[i] += a2[i];
           }
-          tmem_st_wait();
-        }
-        // (b) accumulator 1 -> bias, LeakyReLU, zero outside [0,T), split planes -> mid tile (c2's A operand)
-        {
-          const int t = t0 - p.h2 + m;
-          const bool ok = t >= 0 && t < p.T;
-#pragma unroll
-          for (int c16 = 0; c16 < K::COLS / 16; ++c16) {
-            const int col = col_base + c16 * 16;
-            float a[16], a2[16];
-            tmem_ld16_nowait(acc1 + j * 2 * C + lane_addr + col, a);
-            if (!p.single) tmem_ld16_nowait(acc1 + j * 2 * C + lane_addr + C + col, a2);
-            tmem_wait16(a);
-            if (!p.single) {
-              tmem_wait16(a2);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) a[i] += a2[i];
-            }
-            uint32_t hi[8], lo[8];
+          uint32_t hi[8], lo[8];
+          if (all_ok) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              float y0 = a[2 * jj] * p.inv_s1 + bias_s[col + 2 * jj];
-              float y1 = a[2 * jj + 1] * p.inv_s1 + bias_s[col + 2 * jj + 1];
-              y0 = ok ? fd_act(y0, slope_mid) : 0.f;
-              y1 = ok ? fd_act(y1, slope_mid) : 0.f;
-              fd_split2(y0, y1, PREC, hi[jj], lo[jj]);
+              const float y0 = fmaf(a[2 * jj], p.inv_s1, bias_s[col + 2 * jj]);
+              const float y1 = fmaf(a[2 * jj + 1], p.inv_s1, bias_s[col + 2 * jj + 1]);
+              fd_split2(fmaxf(y0, slope_mid * y0), fmaxf(y1, slope_mid * y1), PREC, hi[jj], lo[jj]);
             }
-            const int kb = col / K::BK_A, cc = col % K::BK_A;
-            const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
+          } else {
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              const uint32_t off = swz((uint32_t)m * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
-              sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
-              sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
+            for (int jj = 0; jj < 8; ++jj) {
+              const float y0 = fmaf(a[2 * jj], p.inv_s1, bias_s[col + 2 * jj]);
+              const float y1 = fmaf(a[2 * jj + 1], p.inv_s1, bias_s[col + 2 * jj + 1]);
+              fd_split2(ok ? fmaxf(y0, slope_mid * y0) : 0.f, ok ? fmaxf(y1, slope_mid * y1) : 0.f, PREC, hi[jj], lo[jj]);
             }
+          }
+          const int kb = col / K::BK_A, cc = col % K::BK_A;
+          const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const uint32_t off = swz((uint32_t)m * K::ROWB + (uint32_t)(cc / 8 + hq) * 16, K::SWZ_A);
+            sts_u4(base + off, hi[hq * 4], hi[hq * 4 + 1], hi[hq * 4 + 2], hi[hq * 4 + 3]);
+            sts_u4(base + K::MID_PLANE_BYTES + off, lo[hq * 4], lo[hq * 4 + 1], lo[hq * 4 + 2], lo[hq * 4 + 3]);
           }
         }
         fence_async_smem();
@@ -538,7 +580,7 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&mid_ready[j]);
-          if (j + K::GROUPS >= MB) mbar_arrive(in_empty);      // this warp's last read of the input tile
+          if (j + K::GROUPS >= MB) mbar_arrive(in_empty);      // GEMM1 of every block has read the input tile, and so has this warp
         }
       }
 
@@ -562,9 +604,9 @@ fd_respair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           }
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj)
-            fd_split2(fd_act(a[2 * jj] * p.inv_s2, p.out_slope) * p.planes_scale,
-                      fd_act(a[2 * jj + 1] * p.inv_s2, p.out_slope) * p.planes_scale, PREC, hi[jj], lo[jj]);
+          for (int jj = 0; jj < 8; ++jj)      // lrelu(a * inv_s2) * planes_scale = max(a * c, a * c * slope), 0 <= slope <= 1
+            fd_split2(fmaxf(a[2 * jj] * out_c, a[2 * jj] * out_cs), fmaxf(a[2 * jj + 1] * out_c, a[2 * jj + 1] * out_cs), PREC,
+                      hi[jj], lo[jj]);
           const int kb = col / K::BK_A, cc = col % K::BK_A;
           const uint32_t base = mid_u + kb * K::MID_KB_BYTES;
 #pragma unroll
@@ -638,9 +680,9 @@ int make_wpair_map(CUtensorMap* m, const uint16_t* ptr, int C, int Ktot, int bkw
   return 0;
 }
 
-template <int C, int PREC, bool MC>
+template <int C, int PREC, bool MC, int EW, int OCC>
 int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) {
-  using K = RpCfg<C>;
+  using K = RpCfg<C, EW, OCC>;
   // tile geometry: MB blocks of 128 rows; the input tile is nbox TMA boxes of rb rows
   const int need = K::ROWS + (p.k1 - 1) * p.d1;
   p.nbox = (need + 255) / 256;
@@ -672,15 +714,16 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   if (rc) return rc;
   rc = make_planes_map(&tout_last, d.out_planes, p.B, p.T, C, K::BK_A, 128 - (p.k2 - 1), 1);
   if (rc) return rc;
-  auto kern = fd_respair_tc_kernel<C, PREC, MC>;
+  auto kern = fd_respair_tc_kernel<C, PREC, MC, EW, OCC>;
   static bool attr_set[FD_MAX_DEVICES] = {false};
   const int dev = fd_current_device();
   if (!attr_set[dev]) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
   const int tiles = p.B * ((p.T + p.r_out - 1) / p.r_out);
-  const int sms = fd_device_sms(dev);
+  const int sms = fd_device_sms(dev) * OCC;
   int grid = tiles < sms ? tiles : sms;
   fd_prof_begin(C == 128 ? 12 : C == 64 ? 13 : C == 32 ? 14 : 15, stream);
   if (MC) {
@@ -703,14 +746,30 @@ int launch_respair(const fd_respair_desc& d, FdResPairK p, cudaStream_t stream) 
   return 0;
 }
 
+template <int C, bool MC, int EW, int OCC>
+int launch_respair_mc(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t stream) {
+  return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16, MC, EW, OCC>(d, p, stream)
+                                  : launch_respair<C, FD_BF16, MC, EW, OCC>(d, p, stream);
+}
+
 template <int C>
 int launch_respair_prec(const fd_respair_desc& d, const FdResPairK& p, cudaStream_t stream) {
   // FD_RP_MCAST(C) names the widths that have the 2-CTA weight-multicast variant; FD_RP_MCAST_ON=0/1 picks at run time
   static const int mc_env = [] { const char* e = getenv("FD_RP_MCAST_ON"); return e ? atoi(e) : -1; }();
-  if (RpCfg<C>::MCAST && mc_env != 0 && (mc_env == 1 || FD_RP_MCAST_DEFAULT))
-    return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16, RpCfg<C>::MCAST>(d, p, stream)
-                                    : launch_respair<C, FD_BF16, RpCfg<C>::MCAST>(d, p, stream);
-  return (d.prec & 0xF) == FD_F16 ? launch_respair<C, FD_F16, false>(d, p, stream) : launch_respair<C, FD_BF16, false>(d, p, stream);
+  // epilogue warps of the stage-major widths (C = 32 / 64): FD_RP_EW=8/16; CTAs per SM at C = 32: FD_RP_OCC=1/2
+  static const int ew_env = [] { const char* e = getenv("FD_RP_EW"); return e ? atoi(e) : FD_RP_EW_DEFAULT; }();
+  static const int occ_env = [] { const char* e = getenv("FD_RP_OCC"); return e ? atoi(e) : FD_RP_OCC_DEFAULT; }();
+  if constexpr (RpCfg<C>::MCAST) {
+    if (mc_env != 0 && (mc_env == 1 || FD_RP_MCAST_DEFAULT)) return launch_respair_mc<C, true, FD_RP_EPI_WARPS(C), 1>(d, p, stream);
+  }
+  if constexpr (C == 32) {
+    if (occ_env == 2) return launch_respair_mc<C, false, 8, 2>(d, p, stream);
+  }
+  if constexpr (C == 32 || C == 64) {
+    if (ew_env == 16) return launch_respair_mc<C, false, 16, 1>(d, p, stream);
+    return launch_respair_mc<C, false, 8, 1>(d, p, stream);
+  }
+  return launch_respair_mc<C, false, FD_RP_EPI_WARPS(C), 1>(d, p, stream);
 }
 
 }  // namespace
@@ -731,7 +790,8 @@ extern "C" int fd_respair_fwd(const fd_respair_desc* d, void* stream) {
              d->C, d->k1, d->d1, d->k2);
   FD_REQUIRE(d->B > 0 && d->T > 0, "fd_respair_fwd: bad shape B=%d T=%d", d->B, d->T);
   FD_REQUIRE(d->in_planes && d->w1 && d->w2 && d->b1 && d->b2 && d->out_planes, "fd_respair_fwd: null pointer");
-  FD_REQUIRE(d->in_slope > 0.f, "fd_respair_fwd: the input LeakyReLU slope must be positive (it is inverted)");
+  FD_REQUIRE(d->in_slope > 0.f && d->in_slope <= 1.f, "fd_respair_fwd: the input LeakyReLU slope must be in (0, 1] (it is inverted)");
+  FD_REQUIRE(d->out_slope >= 0.f && d->out_slope <= 1.f, "fd_respair_fwd: the output LeakyReLU slope must be in [0, 1]");
   FD_REQUIRE((const void*)d->out_planes != (const void*)d->in_planes, "fd_respair_fwd: in-place is not supported (halo reads)");
   FdResPairK p;
   memset(&p, 0, sizeof(p));
@@ -741,6 +801,30 @@ extern "C" int fd_respair_fwd(const fd_respair_desc* d, void* stream) {
   p.inv_s1 = d->w1_inv_scale; p.inv_s2 = d->w2_inv_scale; p.s2 = 1.f / d->w2_inv_scale;
   p.in_slope_inv = 1.f / d->in_slope; p.out_slope = d->out_slope; p.planes_scale = d->planes_scale;
   p.b1 = d->b1; p.b2 = d->b2;
+  {
+    // weight units of BKW channels per tap (BKW as in RpCfg: 32 at C = 128, else min(C, 64)) and their K16 steps
+    const int bkw = d->C == 128 ? 32 : (d->C >= 64 ? 64 : d->C), upt = d->C / bkw, ks = bkw / 16, kst = d->C / 16;
+    FD_REQUIRE(d->k1 * upt <= 64 && d->k2 * upt <= 64, "fd_respair_fwd: more than 64 weight units (k1=%d k2=%d C=%d)", d->k1,
+               d->k2, d->C);
+    auto fill = [&](int k, unsigned long long kmask, unsigned char* ul, int& n, unsigned long long& km) {
+      n = 0; km = 0;
+      const bool masked = kmask != 0ull && k * kst <= 64;
+      if (masked) {
+        for (int u = 0; u < k * upt; ++u) {
+          const unsigned bits = (unsigned)(kmask >> ((u / upt) * kst + (u % upt) * ks)) & ((1u << ks) - 1u);
+          if (bits) { km |= (unsigned long long)bits << (n * ks); ul[n++] = (unsigned char)u; }
+        }
+      }
+      if (n == 0) {                    // dense (or a mask without any set bit inside the conv)
+        for (int u = 0; u < k * upt; ++u) ul[u] = (unsigned char)u;
+        n = k * upt; km = 0;
+        return false;
+      }
+      return true;
+    };
+    const bool m1 = fill(d->k1, d->kmask1, p.ul1, p.n1, p.km1), m2 = fill(d->k2, d->kmask2, p.ul2, p.n2, p.km2);
+    p.masked1 = m1 ? 1 : 0; p.masked2 = m2 ? 1 : 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (d->C) {
     case 128: return launch_respair_prec<128>(*d, p, st);

@@ -396,6 +396,10 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
           } else if (EPI == FD_EPI_RES_SKIP) {
             // residual columns: x' = (x + y)/sqrt2 on the split planes; skip columns: fp32 accumulation.  32-bit element
             // offsets (checked on the host), rows past T clamped for the loads and skipped for the stores.
+            // Tried and dropped (round 2, same-box A/B, B=32 x T=4000): fetching these read-modify-write operands one
+            // chunk ahead (next 32 columns, or the first chunk of the group's next tile) -- 0.408 -> 0.517 ms per launch:
+            // the second operand set pushes the kernel over its 168 registers (104 bytes of spills inside the chunk loop)
+            // and the epilogue is not latency-bound enough to pay for that.
             const bool is_res = n0 < p.C;
             const uint32_t rowbase = (uint32_t)b * (uint32_t)p.T;
             const uint32_t cn = (uint32_t)(is_res ? n : n - p.C);

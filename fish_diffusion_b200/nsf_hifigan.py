@@ -234,7 +234,13 @@ class Generator(nn.Module):
         w2 = W.reshape(F * Co, Kp * F * Ci).contiguous()
         s = N.pow2_scale(w2)
         bias = conv.bias.detach().to(device=device, dtype=torch.float32).repeat(F).contiguous()
-        return dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, K=Kp, d=1, bias=bias, F=F, C=F * Co)
+        # which (tap, 16-input-channel slice) blocks hold weights: most of a folded dilated kernel is zero blocks, which
+        # the fused kernel neither loads nor multiplies (fd_respair_desc.kmask1/2)
+        kmask = 0
+        if (F * Ci) % 16 == 0 and Kp * (F * Ci // 16) <= 64:
+            nz = (W.reshape(F * Co, Kp, F * Ci // 16, 16) != 0).any(dim=3).any(dim=0).reshape(-1).tolist()
+            kmask = sum(1 << i for i, b in enumerate(nz) if b)
+        return dict(w=N.pack_weight(w2, prec, s), inv=1.0 / s, K=Kp, d=1, bias=bias, F=F, C=F * Co, kmask=kmask)
 
     def _pack_convt(self, conv, prec, device):
         """ConvTranspose1d(Ci->Co, k, stride u, padding p) as a polyphase tap-GEMM: output row q of width u*Co
@@ -333,7 +339,7 @@ class Generator(nn.Module):
                 dst = tmp[m % 2] if m < n - 1 else torch.empty_like(PA)
                 N.respair(src, c1["w"], c2["w"], c1["bias"], c2["bias"], B, Lo, Co, c1["K"], c1["d"], c2["K"],
                           out_planes=dst, w1_inv_scale=c1["inv"], w2_inv_scale=c2["inv"], in_slope=LRELU_SLOPE,
-                          out_slope=LRELU_SLOPE, prec=mma)
+                          out_slope=LRELU_SLOPE, prec=mma, kmask1=c1.get("kmask", 0), kmask2=c2.get("kmask", 0))
                 src = dst
             outs.append(src)
         nxt = tmp[0]

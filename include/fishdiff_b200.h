@@ -188,6 +188,10 @@ typedef struct fd_respair_desc {
   float w1_inv_scale, w2_inv_scale;
   float in_slope, out_slope, planes_scale;
   int prec;
+  /* optional block-sparsity hint (0 = dense): bit tap*(C/16) + s set <=> the 16 input channels [16s, 16s+16) of that
+   * tap hold a non-zero weight.  Slices without a bit are neither loaded (whole weight units) nor multiplied; used by
+   * the time-folded C = 16 stage, whose folded kernels are block-sparse.  Ignored when k*(C/16) > 64. */
+  unsigned long long kmask1, kmask2;
 } fd_respair_desc;
 int fd_respair_supported(int C, int k1, int d1, int k2);
 int fd_respair_fwd(const fd_respair_desc* d, void* stream);

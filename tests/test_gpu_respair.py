@@ -38,7 +38,7 @@ def make_case(B, T, C, k, d, seed):
     return x, w1, b1, w2, b2
 
 
-def run_pair(x, w1, b1, w2, b2, k, d, prec="f16", out_slope=SLOPE, planes_scale=1.0):
+def run_pair(x, w1, b1, w2, b2, k, d, prec="f16", out_slope=SLOPE, planes_scale=1.0, kmask1=0, kmask2=0):
     pc = N.prec_code(prec)
     B, T, C = x.shape
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev())
@@ -49,7 +49,7 @@ def run_pair(x, w1, b1, w2, b2, k, d, prec="f16", out_slope=SLOPE, planes_scale=
     out = torch.zeros((2, B, T, C), dtype=torch.int16, device=dev())
     N.respair(pa, w1p, w2p, t(b1), t(b2), B, T, C, k, d, k, out_planes=out, w1_inv_scale=1.0 / s1,
               w2_inv_scale=1.0 / s2, in_slope=SLOPE, out_slope=out_slope, planes_scale=planes_scale,
-              prec=N.mma_code(prec))
+              prec=N.mma_code(prec), kmask1=kmask1, kmask2=kmask2)
     torch.cuda.synchronize()
     ref = pair_ref(planes_to_f64(pa, pc), planes_to_f64(w1p, pc) / s1, b1.astype(np.float64),
                    planes_to_f64(w2p, pc) / s2, b2.astype(np.float64), k, d, k)
@@ -119,3 +119,46 @@ def test_pair_large_batch_many_tiles():
     x, w1, b1, w2, b2 = make_case(4, 40000, C, k, d, 21)
     out, ref, pc = run_pair(x, w1, b1, w2, b2, k, d)
     assert rel_l2(planes_to_f64(out, pc), lrelu(ref)) < 1e-5
+
+
+def block_mask(w, C, k):
+    """fd_respair_desc.kmask: bit tap*(C/16)+s <=> input channels [16s, 16s+16) of that tap hold a non-zero weight."""
+    nz = (w.reshape(C, k, C // 16, 16) != 0).any(axis=(0, 3)).reshape(-1)
+    return sum(1 << i for i, b in enumerate(nz) if b)
+
+
+@pytest.mark.parametrize("C,k,d", [(32, 11, 1), (32, 7, 3), (32, 27, 1), (64, 7, 1), (128, 3, 1)])
+def test_pair_block_sparse_hint(C, k, d):
+    """Block-sparse weights (the shape of the time-folded C = 16 kernels: most (tap, 16-channel) blocks are zero, including
+    the first one) with the sparsity hint: same planes as the dense run of the same weights, and the float64 reference."""
+    if not N.respair_supported(C, k, d, min(k, 17)):
+        pytest.skip("shape outside the kernel's range")
+    k2 = min(k, 7)
+    rng = np.random.RandomState(5 * C + k)
+    x, w1, b1, _, b2 = make_case(2, 700, C, k, d, 77)
+    w2 = (rng.randn(C, k2 * C) / np.sqrt(k2 * C)).astype(np.float32)
+    keep1 = rng.rand(k, C // 16) < 0.4
+    keep1[0, 0] = False                       # the first K16 step of the first tap is skipped: accumulate flag logic
+    keep1[k // 2, :] = True
+    keep2 = rng.rand(k2, C // 16) < 0.6
+    keep2[k2 // 2, 0] = True
+    w1 = (w1.reshape(C, k, C // 16, 16) * keep1[None, :, :, None]).reshape(C, k * C).astype(np.float32)
+    w2 = (w2.reshape(C, k2, C // 16, 16) * keep2[None, :, :, None]).reshape(C, k2 * C).astype(np.float32)
+    pc = N.prec_code("f16")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+    xin = t(x)
+    pa = N.split_nwc(torch.where(xin >= 0, xin, xin * SLOPE), pc)
+    s1, s2 = N.pow2_scale(t(w1)), N.pow2_scale(t(w2))
+    w1p, w2p = N.pack_weight(t(w1), pc, s1), N.pack_weight(t(w2), pc, s2)
+    outs = []
+    for m1, m2 in ((0, 0), (block_mask(w1, C, k), block_mask(w2, C, k2))):
+        out = torch.zeros((2,) + x.shape, dtype=torch.int16, device=dev())
+        N.respair(pa, w1p, w2p, t(b1), t(b2), x.shape[0], x.shape[1], C, k, d, k2, out_planes=out, w1_inv_scale=1.0 / s1,
+                  w2_inv_scale=1.0 / s2, in_slope=SLOPE, out_slope=SLOPE, prec=N.mma_code("f16"), kmask1=m1, kmask2=m2)
+        outs.append(out)
+    torch.cuda.synchronize()
+    ref = pair_ref(planes_to_f64(pa, pc), planes_to_f64(w1p, pc) / s1, b1.astype(np.float64),
+                   planes_to_f64(w2p, pc) / s2, b2.astype(np.float64), k, d, k2)
+    assert rel_l2(planes_to_f64(outs[1], pc), lrelu(ref)) < 1e-5
+    # skipping zero blocks only removes exact zeros from fp32 sums
+    assert rel_l2(planes_to_f64(outs[1], pc), planes_to_f64(outs[0], pc)) < 1e-7

@@ -13,7 +13,12 @@ gen.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic.generator_weig
 g = torch.Generator().manual_seed(0)
 mel = (torch.randn(B, 128, T, generator=g) - 2.5).clamp(-11.5, 2).to(dev)
 f0 = (220.0 * 2 ** (0.3 * torch.sin(torch.arange(T) / 50.0))).repeat(B, 1); f0[:, ::5] = 0; f0 = f0.to(dev)
-for _ in range(int(os.environ.get("N", 2))):
-    gen(mel, f0, seed=1)
+n = int(os.environ.get("N", 2))
+gen(mel, f0, seed=1)                      # packs the weights, sizes the work buffers
 torch.cuda.synchronize()
-print("done")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(n):
+    gen(mel, f0, seed=1)
+e1.record(); torch.cuda.synchronize()
+print(f"done: {e0.elapsed_time(e1) / n:.2f} ms per pass (B={B}, T={T}, {cfg})")
