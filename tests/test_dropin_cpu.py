@@ -230,3 +230,29 @@ def test_oracle_ref_copy_is_verbatim():
             assert hashlib.sha256(f.read()).hexdigest() == man[rel], rel
         with open(os.path.join(here, rel), "rb") as f:
             assert hashlib.sha256(f.read()).hexdigest() == man[rel], rel
+
+
+def test_step_vectors_batched_projection_matches_per_layer_definition():
+    """WaveNet.step_vectors (host torch, differentiable): the batched per-layer diffusion projections equal the reference's
+    per-layer Linear calls (wavenet.py:20-27,107,170-174), values and parameter gradients."""
+    import math
+    import torch.nn.functional as F
+    net = WaveNet(mel_channels=16, d_encoder=32, residual_channels=64, residual_layers=3, use_linear_bias=True, dilation_cycle=2)
+    for p in net.parameters():
+        torch.nn.init.normal_(p, std=0.3)
+    t = torch.tensor([3.0, 250.0, 999.0])
+    d = net.step_vectors(t)
+    half = 32
+    e = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    s = t[:, None] * e[None]
+    s = torch.cat((s.sin(), s.cos()), dim=-1)
+    s = net.mlp[0].linear(s)
+    s = net.mlp[2].linear(s * torch.tanh(F.softplus(s)))
+    want = torch.stack([blk.diffusion_projection.linear(s) for blk in net.residual_layers], dim=1)
+    assert d.shape == (3, 3, 64) and torch.allclose(d, want, rtol=1e-5, atol=1e-5)
+    g = torch.randn_like(d)
+    params = [p for blk in net.residual_layers for p in blk.diffusion_projection.parameters()] + list(net.mlp.parameters())
+    ga = torch.autograd.grad((d * g).sum(), params, retain_graph=True)
+    gb = torch.autograd.grad((want * g).sum(), params)
+    for a, b in zip(ga, gb):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
