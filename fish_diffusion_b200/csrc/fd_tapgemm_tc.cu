@@ -247,6 +247,18 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
         constexpr int HALF = BLOCK_N / 2;       // gate columns | filter columns
         constexpr int PER = HALF / HALVES;      // gate columns handled by this warp
         const int cb = half * PER;
+        // GATE: the bias vectors are read with shared-space loads (through the generic pointers of fd_epi_gate every one of
+        // them was a generic LD and a long-scoreboard stall) and the zero-padding corrections of the first / last `dilation`
+        // rows are skipped by a warp vote where no lane needs them: 81 -> ~60 instructions per element.  Same-box A/B of the
+        // one-product training step: 12.77 / 13.04 -> 12.71 / 12.75 ms, i.e. within noise -- in that mode the kernel is bound by
+        // its operand stream (each 256-column tile re-reads 0.9 MB of weights from L2; 4 ring stages of 48 KB), not by this
+        // epilogue; in the three-product mode the epilogue hides under the MMAs either way.
+        const uint32_t sb = smem_u32(bias_g);
+        const bool e_lo = t < p.dil, e_hi = t + p.dil >= p.T;
+        const bool edge_any = __any_sync(0xffffffffu, valid && (e_lo || e_hi));
+        const size_t zplane = (size_t)p.B * p.T * p.C, zrow = ((size_t)b * p.T + t) * p.C + (size_t)n_tile * HALF;
+        const size_t yplane = (size_t)p.B * p.T * p.n_total, yrow = ((size_t)b * p.T + t) * p.n_total;
+        const int halfg = p.gate_tile / 2;
         for (int c = 0; c < PER; c += 16) {
           const int c0 = cb + c;
           float g[16], f[16];
@@ -257,16 +269,49 @@ fd_tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_c
           if (valid) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              float g8[8], f8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { g8[i] = g[h * 8 + i]; f8[i] = f[h * 8 + i]; }
               const int cc = c0 + h * 8;
-              if (EPI == FD_EPI_MAG)
+              if (EPI == FD_EPI_MAG) {
+                float g8[8], f8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { g8[i] = g[h * 8 + i]; f8[i] = f[h * 8 + i]; }
                 fd_epi_mag<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8);
-              else
-                fd_epi_gate<8, PREC>(p, b, t, n_tile * HALF + cc, g8, f8, bias_g + cc, bias_g + HALF + cc,
-                               bias_g + BLOCK_N + cc, bias_g + BLOCK_N + HALF + cc, bias_g + 2 * BLOCK_N + cc,
-                               bias_g + 2 * BLOCK_N + HALF + cc);
+              } else {
+                float yg[8], yf[8], z[8];
+                {
+                  const float4 a0 = lds128(sb + 4u * cc), a1 = lds128(sb + 4u * cc + 16u);
+                  const float4 b0 = lds128(sb + 4u * (HALF + cc)), b1 = lds128(sb + 4u * (HALF + cc) + 16u);
+                  const float bg[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                  const float bf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    yg[i] = g[h * 8 + i] * p.acc_scale + bg[i];
+                    yf[i] = f[h * 8 + i] * p.acc_scale + bf[i];
+                  }
+                }
+                if (edge_any) {
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    if (e == 0 ? e_lo : e_hi) {
+                      const uint32_t eb = sb + 4u * ((1 + e) * BLOCK_N + cc);
+                      const float4 a0 = lds128(eb), a1 = lds128(eb + 16u);
+                      const float4 b0 = lds128(eb + 4u * HALF), b1 = lds128(eb + 4u * HALF + 16u);
+                      const float eg[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                      const float ef[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) { yg[i] -= eg[i]; yf[i] -= ef[i]; }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = fd_sigmoid(yg[i]) * fd_tanh(yf[i]);
+                if (p.y_planes != nullptr) {   // training: keep the pre-activations (packed column order: gates | filters per tile)
+                  const int zc0 = n_tile * HALF + cc;
+                  const int ng = p.gate_tile == BLOCK_N ? n_tile * BLOCK_N + cc : (zc0 / halfg) * p.gate_tile + (zc0 % halfg);
+                  fd_store_planes<8>(p.y_planes, yplane, yrow + ng, yg, PREC);
+                  fd_store_planes<8>(p.y_planes, yplane, yrow + ng + halfg, yf, PREC);
+                }
+                fd_store_planes<8>(p.out_planes, zplane, zrow + cc, z, PREC);
+              }
             }
           }
         }
@@ -717,6 +762,10 @@ void pick_cfg(const FdTapGemm& p, int* bn, int* bk) {
   if (n < 16) return;
   if (k == 64) {
     if (n < 64) return;
+    // Wave quantisation (a persistent grid runs ceil(tiles / SMs) tile times; at the training shape, 157 row tiles, an N = 512
+    // GEMM is 314 tiles of 256 columns = 3 waves for 2.12 waves of work) was tried against 128-column tiles for LINEAR /
+    // GATE_BWD whenever the quantised time came out > 5 % better: same-box A/B of the training step 12.87 / 12.81 -> 12.81 /
+    // 12.80 ms (one product), 19.84 / 20.07 -> 19.87 / 19.66 ms (three products) -- noise; left out.
     *bn = n; *bk = 64;
   } else if (k == 32) {
     if (p.epi != FD_EPI_LINEAR || n < 32) return;   // (GATE_BWD: BLOCK_K 64 only)

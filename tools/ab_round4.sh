@@ -1,0 +1,18 @@
+#!/bin/bash
+# GATE epilogue rewrite: parity tests, then same-box A/B of the training step and of a short sampler run
+mkdir -p gpurun_out
+L=gpurun_out/ab_round4.log
+: > $L
+OLD=$PWD/build/ab/libfishdiff_old.so
+run() { echo "=== $1" >> $L; shift; env "$@" >> $L 2>&1; }
+run "tests new" timeout 900 python -m pytest tests/test_gpu_tapgemm.py tests/test_gpu_wavenet.py tests/test_gpu_train.py tests/test_gpu_r2_golden.py tests/test_gpu_fullsize.py -x -q
+S="python bench.py --steps 2 --warmup 3 --evals 20 --no-vocoder --no-cpu-baseline --no-e2e --no-train --no-extras"
+for rep in 1 2; do
+  run "train x1 old rep$rep" FISHDIFF_B200_LIB=$OLD timeout 300 python tools/bench_train.py --steps 20 --warmup 5 --precision f16x1
+  run "train x1 new rep$rep" timeout 300 python tools/bench_train.py --steps 20 --warmup 5 --precision f16x1
+  run "train f16 old rep$rep" FISHDIFF_B200_LIB=$OLD timeout 300 python tools/bench_train.py --steps 10 --warmup 3 --precision f16
+  run "train f16 new rep$rep" timeout 300 python tools/bench_train.py --steps 10 --warmup 3 --precision f16
+  run "sampler old rep$rep" FISHDIFF_B200_LIB=$OLD timeout 300 $S
+  run "sampler new rep$rep" timeout 300 $S
+done
+grep -E "passed|failed|error" $L | head; grep -E "^=== |ms_per_step" $L | sed -E 's/.*"ms_per_step": ([0-9.]+).*/   \1/' | paste - - | head -20
