@@ -124,6 +124,7 @@ _SIGS = {
                                                                                    c_int, c_int, c_void_p]),
     "fd_gate_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_int, c_int, c_int, c_void_p]),
     "fd_relu_bwd": (c_int, [c_void_p] * 3 + [c_longlong, c_float, c_int, c_void_p]),
+    "fd_lrelu_bwd": (c_int, [c_void_p] * 5 + [c_longlong, c_float, c_float, c_int, c_void_p]),
     "fd_colsum": (c_int, [c_void_p] * 3 + [c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "fd_reduce_batch": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_float, c_void_p]),
     "fd_abi_version": (c_int, []),
@@ -456,3 +457,20 @@ def wgrad_cl(row_srcs, col_srcs, row_segs, col_segs, B, T, *, scale=1.0, prec=PR
     assert tuple(out.shape) == (R, Cc) and out.dtype == torch.float32
     check(lib().fd_reduce_batch(ptr(part), ptr(out), splits, R * Cc, float(scale), st), "fd_reduce_batch")
     return out
+
+
+def lrelu_bwd(grad, act_planes, slope, *, addend=None, out_f32=None, out_planes=None, scale=1.0, prec=PREC_F16):
+    """v = grad * (act > 0 ? 1 : slope) * scale + addend -> out_f32 and / or out_planes (fd_lrelu_bwd).
+    grad / addend / out_f32: fp32 tensors of n elements, act_planes / out_planes: split planes [2, n]."""
+    n = grad.numel()
+    assert act_planes.numel() == 2 * n and (out_f32 is not None or out_planes is not None)
+    check(lib().fd_lrelu_bwd(ptr(grad), ptr(act_planes), ptr(addend), ptr(out_f32), ptr(out_planes), n, float(slope),
+                             float(scale), prec, stream_ptr(grad.device)), "fd_lrelu_bwd")
+
+
+def colsum(planes, B, T, Nn, *, scale=1.0, prec=PREC_F16):
+    """sum over (b, t) of planes [2,B,T,Nn] * scale -> fp32 [Nn]  (fd_colsum per item, then a sum over the items)."""
+    out = torch.zeros((B, Nn), dtype=torch.float32, device=planes.device)
+    check(lib().fd_colsum(ptr(planes), None, ptr(out), B, T, Nn, float(scale), prec, stream_ptr(planes.device)),
+          "fd_colsum")
+    return out.sum(0)

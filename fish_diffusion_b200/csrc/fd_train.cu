@@ -104,6 +104,31 @@ __global__ void k_relu_bwd(const float* __restrict__ grad, const uint16_t* __res
   }
 }
 
+// LeakyReLU backward with an optional addend (autograd of `x + c2(lrelu(c1(lrelu(x))))`, nsf_hifigan/models.py:103-110):
+//   v = grad * (act > 0 ? 1 : slope) * scale + addend      act = planes of lrelu(x) (same sign as x)
+// -> out_f32 and / or out_planes (either may be null, not both)
+__global__ void k_lrelu_bwd(const float* __restrict__ grad, const uint16_t* __restrict__ act,
+                            const float* __restrict__ addend, float* __restrict__ out_f32,
+                            uint16_t* __restrict__ out_planes, long long n, float slope, float scale, int prec) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    float a[4], g[4];
+    fd_load_planes<4>(act, (size_t)n, (size_t)e, a, prec);
+    fd_load_f32<4>(grad + e, g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = (a[k] > 0.f ? g[k] : g[k] * slope) * scale;
+    if (addend != nullptr) {
+      float r[4];
+      fd_load_f32<4>(addend + e, r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] += r[k];
+    }
+    if (out_f32 != nullptr) fd_store_f32<4>(out_f32 + e, g);
+    if (out_planes != nullptr) fd_store_planes<4>(out_planes, (size_t)n, (size_t)e, g, prec);
+  }
+}
+
 // column sums per batch item: in (planes [2][B][T][N] or fp32 [B][T][N]) -> out[b][n] += scale * sum_t in[b,t,n]
 // (out must be zero-initialised; fp32 atomics over the row chunks)
 __global__ void k_colsum(const uint16_t* __restrict__ planes, const float* __restrict__ f32, float* __restrict__ out,
@@ -198,6 +223,18 @@ int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_pla
   FD_DEVICE_GUARD();
   FD_REQUIRE(n % 4 == 0, "fd_relu_bwd: n=%lld must be a multiple of 4", n);
   k_relu_bwd<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>(grad, act_planes, out_planes, n, scale, prec);
+  FD_LAUNCHED();
+  return 0;
+}
+
+int fd_lrelu_bwd(const float* grad, const uint16_t* act_planes, const float* addend, float* out_f32,
+                 uint16_t* out_planes, long long n, float slope, float scale, int prec, void* stream) {
+  FD_DEVICE_GUARD();
+  FD_REQUIRE(n > 0 && n % 4 == 0, "fd_lrelu_bwd: n=%lld must be a positive multiple of 4", n);
+  FD_REQUIRE(grad != nullptr && act_planes != nullptr && (out_f32 != nullptr || out_planes != nullptr),
+             "fd_lrelu_bwd: grad, act_planes and at least one output are required");
+  k_lrelu_bwd<<<grid1d(n / 4), 256, 0, (cudaStream_t)stream>>>(grad, act_planes, addend, out_f32, out_planes, n, slope,
+                                                               scale, prec);
   FD_LAUNCHED();
   return 0;
 }

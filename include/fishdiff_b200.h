@@ -327,6 +327,12 @@ int fd_gate_bwd(const float* dz, const uint16_t* y_planes, uint16_t* dy_planes, 
 /* out planes = split(grad * (act_planes > 0) * scale) (ReLU backward, wavenet.py:212,230) */
 int fd_relu_bwd(const float* grad, const uint16_t* act_planes, uint16_t* out_planes, long long n, float scale, int prec,
                 void* stream);
+/* LeakyReLU backward with an optional addend -- autograd of one ResBlock1 iteration `x + c2(lrelu(c1(lrelu(x))))`
+ * (nsf_hifigan/models.py:103-110; vocoder training, tools/nsf_hifigan/train.py:114-231):
+ *   v = grad * (act > 0 ? 1 : slope) * scale + addend,   act_planes = planes of lrelu(x) (same sign as x)
+ * written to out_f32 and / or out_planes (one of them may be NULL); addend may be NULL; n a multiple of 4. */
+int fd_lrelu_bwd(const float* grad, const uint16_t* act_planes, const float* addend, float* out_f32,
+                 uint16_t* out_planes, long long n, float slope, float scale, int prec, void* stream);
 /* out[b][n] += scale * sum_t in[b,t,n]  (bias / step-vector gradients); exactly one of planes / f32 is non-NULL;
  * out must be zero-initialised by the caller */
 int fd_colsum(const uint16_t* planes, const float* f32, float* out, int B, int T, int N, float scale, int prec,
