@@ -350,3 +350,81 @@ class ConvTranspose1dFn(torch.autograd.Function):
             N.conv_cl(Gp, pk["bwd"], B, L, NN, Ci, [-d for d in deltas], w_inv_scale=pk["inv"] * inv, out_f32=dx,
                       prec=mma, backend=_backend(Ci, NN, len(deltas), cfg.backend))
         return None, None, None, dx, gw, gb
+
+
+# ------------------------------------------------------------------------------------------------ generator
+@torch.no_grad()
+def sine_waves(f0_up, sgen, rand_ini=None, noise=None):
+    """SineGen.forward (models.py:201-294; its body runs under no_grad in the reference too): f0_up [B,S,1] in Hz ->
+    harmonic bank + noise [B,S,H].  Torch ops: in training the H-wide bank is needed as the operand of the l_linear
+    weight gradient (the inference kernel fd_sinegen_fwd emits only tanh(l_linear(.))).
+    rand_ini [B,H] (column 0 is forced to 0) and noise [B,S,H] may be injected by parity tests."""
+    B, S, _ = f0_up.shape
+    H = sgen.dim
+    mult = torch.arange(1, H + 1, device=f0_up.device, dtype=f0_up.dtype)
+    f0_buf = f0_up * mult                                            # fundamental and overtones
+    rad = (f0_buf / sgen.sampling_rate) % 1
+    ri = torch.rand(B, H, device=f0_up.device) if rand_ini is None else rand_ini.to(f0_up).clone()
+    ri[:, 0] = 0
+    rad[:, 0, :] = rad[:, 0, :] + ri
+    over = torch.cumsum(rad, 1) % 1                                  # -1 wherever the running phase wraps
+    wrapped = (over[:, 1:, :] - over[:, :-1, :]) < 0
+    shift = torch.zeros_like(rad)
+    shift[:, 1:, :] = wrapped * -1.0
+    sines = torch.sin(torch.cumsum(rad + shift, dim=1) * 2 * math.pi) * sgen.sine_amp
+    uv = (f0_up > sgen.voiced_threshold).to(f0_up.dtype)
+    amp = uv * sgen.noise_std + (1 - uv) * sgen.sine_amp / 3
+    nz = amp * (torch.randn_like(sines) if noise is None else noise.to(sines))
+    return sines * uv + nz
+
+
+def generator_forward_train(gen, mel, f0, cfg=None, rand_ini=None, sine_noise=None):
+    """Differentiable Generator.forward (models.py:407-438) for the vocoder training step
+    (tools/nsf_hifigan/train.py:124, `self.generator(mels, pitches)`): mel [B,M,T], f0 [B,T] or [B,1,T] -> wav [B,1,T*hop].
+
+    conv_pre, every ups[i] and every ResBlock1 (>= 97 % of the FLOPs) run forward AND backward on the native nodes above,
+    channels-last throughout; the one-channel ends of the network stay torch ops under autograd: the harmonic source
+    (l_linear + tanh over the sine bank), noise_convs[i] (1 -> C strided convs of the excitation), the LeakyReLUs between
+    nodes, conv_post (C -> 1) + tanh.  `gen` is a fish_diffusion_b200.Generator with or without weight-norm."""
+    from torch.nn import functional as Fn
+    from .nsf_hifigan import ResBlock1, _effective_weight
+    N.require_cuda(mel, "mel")
+    if cfg is None:
+        cfg = TrainCfg(getattr(gen, "precision", "f16"), "auto")
+    if f0.ndim == 2:
+        f0 = f0[:, None]
+    B, M, T = mel.shape
+    hop = 1
+    for u in gen.h.upsample_rates:
+        hop *= int(u)
+    hs = getattr(gen.h, "hop_size", hop)
+    if hs != hop:
+        raise ValueError(f"hop_size {hs} != product of upsample_rates {hop}")
+    f0_up = Fn.interpolate(f0.to(torch.float32), size=T * hop, mode="linear").transpose(1, 2)      # [B,S,1]
+    bank = sine_waves(f0_up, gen.m_source.l_sin_gen, rand_ini=rand_ini, noise=sine_noise)
+    har = torch.tanh(gen.m_source.l_linear(bank)).transpose(1, 2)                                 # [B,1,S]
+
+    x = Conv1dFn.apply(cfg, 1, mel.to(torch.float32).transpose(1, 2).contiguous(), _effective_weight(gen.conv_pre),
+                       gen.conv_pre.bias)                                                          # [B,T,C0]
+    nk = gen.num_kernels
+    for i in range(gen.num_upsamples):
+        up, nc = gen.ups[i], gen.noise_convs[i]
+        x = Fn.leaky_relu(x, LRELU_SLOPE)
+        x = ConvTranspose1dFn.apply(cfg, up.stride[0], up.padding[0], x, _effective_weight(up), up.bias)
+        x = x + Fn.conv1d(har, nc.weight, nc.bias, stride=nc.stride, padding=nc.padding).transpose(1, 2)
+        xs = None
+        for j in range(nk):
+            rb = gen.resblocks[i * nk + j]
+            if not isinstance(rb, ResBlock1):
+                raise NotImplementedError("generator_forward_train: only ResBlock1 generators (resblock: \"1\", every "
+                                          "shipped training config) have a native backward")
+            wb = []
+            for c1, c2 in zip(rb.convs1, rb.convs2):
+                wb += [_effective_weight(c1), c1.bias, _effective_weight(c2), c2.bias]
+            y = ResBlock1Fn.apply(cfg, tuple(rb.dilation), x, *wb)
+            xs = y if xs is None else xs + y
+        x = xs / nk
+    x = Fn.leaky_relu(x)                                              # default slope 0.01 (models.py:434)
+    post = gen.conv_post
+    wav = Fn.conv1d(x.transpose(1, 2), _effective_weight(post), post.bias, padding=post.padding)
+    return torch.tanh(wav)
