@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-voc-train", action="store_true", help="skip the vocoder-training side measurement (N4)")
     ap.add_argument("--no-extras", action="store_true", help="skip unipc / single-product / strong-scaling side runs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -470,6 +471,25 @@ def main():
         except Exception as ex:  # noqa: BLE001
             train = {"error": repr(ex)[:400]}
 
+    # ---- vocoder training (config_v1_256, batch 20 x 32768 samples as configs/vocoder_nsf_hifigan.py):
+    #      generator forward + backward on the native nodes next to the reference class under cuDNN autograd on the same
+    #      GPU and on the host cores, and one whole GAN step (tools/bench_voc_train.py)
+    voc_train = None
+    if rank == 0 and world == 1 and not args.no_voc_train:
+        torch.cuda.empty_cache()
+        try:
+            import importlib.util
+            import types as _types
+            spec = importlib.util.spec_from_file_location(
+                "bench_voc_train", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_voc_train.py"))
+            bvt = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bvt)
+            voc_train = bvt.measure(_types.SimpleNamespace(batch=20, frames=128, steps=3, cpu=not args.no_cpu_baseline,
+                                                           no_step=False))
+        except Exception as ex:  # noqa: BLE001
+            voc_train = {"error": repr(ex)[:400]}
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -504,7 +524,7 @@ def main():
             "gpu_launches_note": f"{launches_per_step} kernels of this library per sampler run (counted on an eager run); "
                                  f"inside the timed region {launches} went through the launch counter, the rest were "
                                  f"replayed from CUDA graphs of the same launch sequence",
-            "roofline": roof, "cpu_baseline": cpu, "vocoder": voc, "train": train,
+            "roofline": roof, "cpu_baseline": cpu, "vocoder": voc, "train": train, "voc_train": voc_train,
             "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
         }
         line.update(extras)

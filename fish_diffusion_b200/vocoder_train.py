@@ -378,14 +378,46 @@ def sine_waves(f0_up, sgen, rand_ini=None, noise=None):
     return sines * uv + nz
 
 
+def excitation_conv(har, weight, bias, stride, padding):
+    """noise_convs[i] (models.py:380-393, 422): Conv1d(1 -> C, k, stride, padding) of the excitation har [B,S] ->
+    channels-last [B, Lo, C], written as windows @ weight^T.  A float32 matmul is exact float32 arithmetic under torch's
+    default matmul precision, whereas cuDNN convolutions default to TF32 (measured: 9e-4 on the generated audio)."""
+    k = weight.shape[-1]
+    hp = torch.nn.functional.pad(har, (padding, padding))
+    w = weight[:, 0, :]                                                                   # [C, k]
+    n_out = (hp.shape[-1] - k) // stride + 1
+    if k % stride == 0 and hp.shape[-1] == (n_out - 1) * stride + k:
+        # every shipped config: k = 2*stride (or 1): window t = blocks t .. t + k/stride - 1 of `stride` samples
+        blocks = hp.view(hp.shape[0], -1, stride)                                         # [B, Lo + k/s - 1, s]
+        out = bias
+        for q in range(k // stride):
+            out = out + torch.matmul(blocks[:, q:q + n_out], w[:, q * stride:(q + 1) * stride].t())
+        return out
+    return torch.matmul(hp.unfold(-1, k, stride), w.t()) + bias                           # [B, Lo, k] strided view
+
+
+def post_conv(x_cl, weight, bias):
+    """conv_post (models.py:403, 435): Conv1d(C -> 1, k, 'same') on channels-last x [B,S,C] -> [B,1,S], as one matmul
+    x @ W [C,k] followed by the sum of the k shifted columns (exact float32, see excitation_conv)."""
+    B, S, C = x_cl.shape
+    k = weight.shape[-1]
+    half = (k - 1) // 2
+    cols = torch.nn.functional.pad(torch.matmul(x_cl, weight[0]), (0, 0, half, half))       # [B, S + 2*half, k]
+    out = bias.view(1, 1).expand(B, S)
+    for j in range(k):
+        out = out + cols[:, j:j + S, j]
+    return out[:, None, :]
+
+
 def generator_forward_train(gen, mel, f0, cfg=None, rand_ini=None, sine_noise=None):
     """Differentiable Generator.forward (models.py:407-438) for the vocoder training step
     (tools/nsf_hifigan/train.py:124, `self.generator(mels, pitches)`): mel [B,M,T], f0 [B,T] or [B,1,T] -> wav [B,1,T*hop].
 
     conv_pre, every ups[i] and every ResBlock1 (>= 97 % of the FLOPs) run forward AND backward on the native nodes above,
     channels-last throughout; the one-channel ends of the network stay torch ops under autograd: the harmonic source
-    (l_linear + tanh over the sine bank), noise_convs[i] (1 -> C strided convs of the excitation), the LeakyReLUs between
-    nodes, conv_post (C -> 1) + tanh.  `gen` is a fish_diffusion_b200.Generator with or without weight-norm."""
+    (l_linear + tanh over the sine bank), noise_convs[i] (1 -> C strided convs of the excitation, as matmuls), the
+    LeakyReLUs between nodes, conv_post (C -> 1, as a matmul) + tanh.  `gen` is a fish_diffusion_b200.Generator with or
+    without weight-norm."""
     from torch.nn import functional as Fn
     from .nsf_hifigan import ResBlock1, _effective_weight
     N.require_cuda(mel, "mel")
@@ -402,7 +434,7 @@ def generator_forward_train(gen, mel, f0, cfg=None, rand_ini=None, sine_noise=No
         raise ValueError(f"hop_size {hs} != product of upsample_rates {hop}")
     f0_up = Fn.interpolate(f0.to(torch.float32), size=T * hop, mode="linear").transpose(1, 2)      # [B,S,1]
     bank = sine_waves(f0_up, gen.m_source.l_sin_gen, rand_ini=rand_ini, noise=sine_noise)
-    har = torch.tanh(gen.m_source.l_linear(bank)).transpose(1, 2)                                 # [B,1,S]
+    har = torch.tanh(gen.m_source.l_linear(bank))[:, :, 0]                                        # [B,S]
 
     x = Conv1dFn.apply(cfg, 1, mel.to(torch.float32).transpose(1, 2).contiguous(), _effective_weight(gen.conv_pre),
                        gen.conv_pre.bias)                                                          # [B,T,C0]
@@ -411,7 +443,7 @@ def generator_forward_train(gen, mel, f0, cfg=None, rand_ini=None, sine_noise=No
         up, nc = gen.ups[i], gen.noise_convs[i]
         x = Fn.leaky_relu(x, LRELU_SLOPE)
         x = ConvTranspose1dFn.apply(cfg, up.stride[0], up.padding[0], x, _effective_weight(up), up.bias)
-        x = x + Fn.conv1d(har, nc.weight, nc.bias, stride=nc.stride, padding=nc.padding).transpose(1, 2)
+        x = x + excitation_conv(har, nc.weight, nc.bias, nc.stride[0], nc.padding[0])
         xs = None
         for j in range(nk):
             rb = gen.resblocks[i * nk + j]
@@ -425,6 +457,4 @@ def generator_forward_train(gen, mel, f0, cfg=None, rand_ini=None, sine_noise=No
             xs = y if xs is None else xs + y
         x = xs / nk
     x = Fn.leaky_relu(x)                                              # default slope 0.01 (models.py:434)
-    post = gen.conv_post
-    wav = Fn.conv1d(x.transpose(1, 2), _effective_weight(post), post.bias, padding=post.padding)
-    return torch.tanh(wav)
+    return torch.tanh(post_conv(x, _effective_weight(gen.conv_post), gen.conv_post.bias))

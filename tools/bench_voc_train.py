@@ -40,7 +40,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--no-step", action="store_true")
-    a = ap.parse_args()
+    print(json.dumps(measure(ap.parse_args())))
+
+
+def measure(a):
+    """a: namespace(batch, frames, steps, cpu, no_step) -> dict (see the module docstring)."""
     from fish_diffusion_b200 import Generator, _native as N
     from fish_diffusion_b200 import vocoder_train as VT
     with open(os.path.join(ROOT, "tests", "golden", "nsf_configs", "config_v1_256.json")) as f:
@@ -90,9 +94,12 @@ def main():
             torch.backends.cudnn.allow_tf32 = tf32
             torch.backends.cuda.matmul.allow_tf32 = tf32
             out[f"reference_cudnn_gen_fwd_bwd_{tag}"] = {"ms": timed(ref_step, a.steps)}
-        torch.backends.cudnn.allow_tf32 = True
+        del rg
     except Exception as e:  # noqa: BLE001
         out["reference_cudnn_gen_fwd_bwd"] = {"error": repr(e)[:300]}
+    finally:
+        torch.backends.cudnn.allow_tf32 = True          # torch's defaults
+        torch.backends.cuda.matmul.allow_tf32 = False
 
     if not a.no_step:
         try:
@@ -122,6 +129,7 @@ def main():
         try:
             from oracle import ref_loader
             ref = ref_loader.load_reference(with_mel=False)
+            threads0 = torch.get_num_threads()
             torch.set_num_threads(os.cpu_count() // 2 or 1)
             rc = ref.nsf.Generator(ref.nsf.AttrDict(h))
             bc = min(B, 2)
@@ -134,9 +142,10 @@ def main():
             dt = time.perf_counter() - t0
             out["reference_cpu_gen_fwd_bwd"] = {"ms": dt * 1e3, "batch": bc, "threads": torch.get_num_threads(),
                                                 "ms_scaled_to_batch": dt * 1e3 * B / bc}
+            torch.set_num_threads(threads0)
         except Exception as e:  # noqa: BLE001
             out["reference_cpu_gen_fwd_bwd"] = {"error": repr(e)[:300]}
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
