@@ -143,19 +143,24 @@ def main():
             i += 1
     np.savez_compressed(os.path.join(HERE, "n4_train.npz"), **out)
     print("n4_train.npz:", os.path.getsize(os.path.join(HERE, "n4_train.npz")) // 1024, "KiB,", i, "gradients")
-    gold_generator_grads(ref, sd, out["mels"], out["pitches"])
+    gold_generator_grads(ref, sd, out["mels"], out["pitches"], 1.0, "n4_gen.npz")
+    # the checkpoint holds 3x the reference's initial weights (round-2 golden: audible output), which saturates the final
+    # tanh (rms 0.9998); a third of it is the reference's own initialisation -- a well-conditioned operating point
+    gold_generator_grads(ref, {k: v / 3 for k, v in sd.items()}, out["mels"], out["pitches"], 1.0 / 3, "n4_gen_init.npz")
 
 
-def gold_generator_grads(ref, sd, mels, pitches):
+def gold_generator_grads(ref, sd, mels, pitches, scale, fname):
     """n4_gen.npz: gradients of the reference Generator (weight-norm parameters) under a SMOOTH loss sum(wav * gw), from
     the reference module in FLOAT64 (the arbiter).  Why float64 and why loose tolerances downstream:
     at this operating point the gradient is ill-conditioned -- LeakyReLU masks of near-zero activations flip under 1e-7
     forward noise -- and the reference's own float32 runs disagree with each other (1 thread vs 8 threads of oneDNN: 2e-5 on
     the audio, 1.1e-2 on the worst parameter gradient, 2.6e-3 median) and with float64 (1-thread float32: 1.4e-3 worst,
-    9e-4 median).  The stored `noise_*` keys record that floor.  The training losses proper (L1 / max-pool terms) are
+    9e-4 median).  The stored `noise_*` keys record that floor.  That is the 3x-initialisation checkpoint, whose output
+    saturates the final tanh; at the reference's own initialisation (weights / 3, `n4_gen_init.npz`) the same comparison is
+    well conditioned (float32 vs float64: 7e-8 on the audio, 3.5e-6 worst gradient) and pins the backward tightly.  The training losses proper (L1 / max-pool terms) are
     even less smooth: dL/d(audio) moves by ~6 % under a 1e-7 perturbation of the generated audio."""
     h = nu.train_config()
-    out = {"mels": mels, "pitches": pitches, "gw_seed": np.array(4400)}
+    out = {"mels": mels, "pitches": pitches, "gw_seed": np.array(4400), "weight_scale": np.float64(scale)}
     gw = np.random.RandomState(4400).randn(mels.shape[0], 1, mels.shape[2] * h["hop_size"])
     runs = {}
     for tag, dt, nt in (("f64", torch.float64, 8), ("f32", torch.float32, 8), ("f32_1t", torch.float32, 1)):
@@ -179,8 +184,9 @@ def gold_generator_grads(ref, sd, mels, pitches):
         out[f"noise_{tag}_wav"] = np.float64(np.linalg.norm(w - wav64) / np.linalg.norm(wav64))
         out[f"noise_{tag}_grad_worst"], out[f"noise_{tag}_grad_median"] = np.float64(errs[-1]), np.float64(errs[len(errs) // 2])
         print(f"  reference {tag} vs f64: wav {out[f'noise_{tag}_wav']:.2e}, grads worst {errs[-1]:.2e} median {errs[len(errs) // 2]:.2e}")
-    np.savez_compressed(os.path.join(HERE, "n4_gen.npz"), **out)
-    print("n4_gen.npz:", os.path.getsize(os.path.join(HERE, "n4_gen.npz")) // 1024, "KiB")
+    out["wav_rms"] = np.float64(np.sqrt(np.mean(wav64 ** 2)))
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+    print(f"{fname}: {os.path.getsize(os.path.join(HERE, fname)) // 1024} KiB, wav rms {out['wav_rms']:.4f}")
 
 
 if __name__ == "__main__":

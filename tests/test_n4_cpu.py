@@ -147,17 +147,20 @@ def _draws(seed, shapes):
     return [torch.from_numpy((rng.rand(*s) if i == 0 else rng.randn(*s)).astype(np.float32)) for i, s in enumerate(shapes)]
 
 
-def test_generator_gradients_vs_reference_golden(golden):
+@pytest.mark.parametrize("name,wav_tol,worst_tol,median_tol", [("n4_gen_init", 1e-6, 5e-3, 1e-4), ("n4_gen", 1e-4, 1.5e-2, 4e-3)])
+def test_generator_gradients_vs_reference_golden(golden, name, wav_tol, worst_tol, median_tol):
     """Host logic of the differentiable generator (emulated device primitives) against the float64 reference Generator's
-    autograd under a smooth loss: every weight-norm parameter gradient.  Tolerances sit at the reference's own float32 noise
-    on this golden (stored: 8-thread float32 vs float64 worst 9.9e-3 / median 2.6e-3, 1-thread 1.4e-3 / 8.6e-4): LeakyReLU
-    masks of near-zero activations flip under 1e-7 forward noise.  The tight check of the backward algebra is the
-    node-level tests above (1e-6 against torch autograd)."""
+    autograd under a smooth loss: every weight-norm parameter gradient.
+      n4_gen_init  the reference's own initialisation (checkpoint / 3): well conditioned, the reference's float32 runs sit
+                   7e-8 (audio) / 3.6e-6 worst gradient from float64 -- apart from single LeakyReLU mask flips of near-zero
+                   activations, which move one conv's gradients by ~5e-4 (seen in the reference's 8-thread run as well);
+      n4_gen       3x those weights: the final tanh saturates (rms 0.9998) and the gradient is chaotic -- the reference's own
+                   float32 runs disagree with float64 by 9.9e-3 worst / 2.6e-3 median (8 threads), 1.4e-3 / 8.6e-4 (1)."""
     from fish_diffusion_b200 import Generator
     from fish_diffusion_b200 import vocoder_train as VT
-    g = golden("n4_gen")
+    g = golden(name)
     gen = Generator(nu.train_config())
-    gen.load_state_dict(_load_ckpt_generator(), strict=True)
+    gen.load_state_dict({k: v * float(g["weight_scale"]) for k, v in _load_ckpt_generator().items()}, strict=True)
     mel, f0 = torch.from_numpy(g["mels"]), torch.from_numpy(g["pitches"])
     B, S = mel.shape[0], mel.shape[2] * 64
     ri, nz = _draws(nu.SEED_DRAWS + 1, [(B, 9), (B, S, 9)])
@@ -166,10 +169,10 @@ def test_generator_gradients_vs_reference_golden(golden):
         wav = VT.generator_forward_train(gen, mel, f0, VT.TrainCfg("f16"), rand_ini=ri, sine_noise=nz)
         (wav * gw).sum().backward()
     e_wav = rel(wav, torch.from_numpy(g["wav"]))
-    print(f"wav vs float64 reference {e_wav:.2e} (reference float32: {float(g['noise_f32_wav']):.2e})")
-    assert e_wav < 1e-4
-    nu.check_gradients(g, [(n, p.grad.numpy()) for n, p in gen.named_parameters()], "grad_", 1.5e-2, 4e-3,
-                       "generator gradients (emulated primitives) vs float64 reference")
+    print(f"[{name}] wav vs float64 reference {e_wav:.2e} (reference float32: {float(g['noise_f32_wav']):.2e})")
+    assert e_wav < wav_tol
+    nu.check_gradients(g, [(n, p.grad.numpy()) for n, p in gen.named_parameters()], "grad_", worst_tol, median_tol,
+                       f"[{name}] generator gradients (emulated primitives) vs float64 reference")
 
 
 def test_training_step_vs_reference_golden(golden):
