@@ -16,5 +16,8 @@ from .diffsinger import ENCODERS, DiffSinger, NaiveProjectionEncoder, load_check
 from .fastspeech import FastSpeech2Encoder  # noqa: F401
 from .pipeline import BatchedSynthesizer, plan_batches  # noqa: F401
 from . import formats  # noqa: F401
+from .vocoder_gan import (HifiGanTrainer, MultiPeriodDiscriminator, MultiScaleDiscriminator,  # noqa: F401
+                          average_gradients)
+from .vocoder_train import generator_forward_train  # noqa: F401
 
 __version__ = "0.1.0"

@@ -182,6 +182,24 @@ def log_mel(transform, audio):
     return torch.log(torch.clamp(transform(audio.squeeze(1)), min=1e-5))
 
 
+def average_gradients(params, group=None):
+    """The gradient all-reduce of the reference's DDPStrategy (configs/vocoder_nsf_hifigan.py:25, NCCL over NVLink): one
+    flat average of every gradient present -- pass it as `reduce_grads` to HifiGanTrainer.training_step, one process per
+    GPU.  (`find_unused_parameters=True` there exists because each backward touches only one of the two networks; here the
+    hook is called per network.)"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    for g, r in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(r)
+
+
 # ------------------------------------------------------------------------------------------------ trainer
 class HifiGanTrainer(nn.Module):
     """The HSFHifiGAN role (train.py:32-231).  `h`: the JSON config (dict); attribute names follow the reference
@@ -216,9 +234,11 @@ class HifiGanTrainer(nn.Module):
     def configure_optimizers(self):
         h = self.h
         betas = (h.adam_b1, h.adam_b2)
-        self.optim_g = torch.optim.AdamW(self.generator.parameters(), lr=h.learning_rate, betas=betas)
+        # the reference's torch.optim.AdamW (default weight decay); on CUDA its fused single-kernel implementation
+        fused = all(p.is_cuda for p in self.parameters())
+        self.optim_g = torch.optim.AdamW(self.generator.parameters(), lr=h.learning_rate, betas=betas, fused=fused)
         self.optim_d = torch.optim.AdamW(itertools.chain(self.msd.parameters(), self.mpd.parameters()),
-                                         lr=h.learning_rate, betas=betas)
+                                         lr=h.learning_rate, betas=betas, fused=fused)
         self.sched_g = torch.optim.lr_scheduler.ExponentialLR(self.optim_g, h.lr_decay)
         self.sched_d = torch.optim.lr_scheduler.ExponentialLR(self.optim_d, h.lr_decay)
         return [self.optim_g, self.optim_d], [self.sched_g, self.sched_d]
@@ -284,6 +304,20 @@ class HifiGanTrainer(nn.Module):
             reduce_grads(self.generator.parameters())
         self.optim_g.step()
         return dict(loss_disc=float(loss_d.detach()), loss_gen=float(loss_g.detach()), **parts)
+
+    @torch.no_grad()
+    def validation_step(self, batch, **gen_kw):
+        """train.py:241-270: masked L1 between the log-mel of the target and of the generated audio -> float.  No gradient
+        is needed here, so the generator runs its inference path (fused ResBlock-pair kernels, nsf_hifigan.Generator.forward)
+        and both mels come from the native front end."""
+        pitches, audios = batch["pitches"].float(), batch["audio"].float()
+        mel_lens = batch["audio_lens"] // self.h.hop_size
+        n_frames = int(mel_lens.max())
+        mels = batch["mels"][:, :, :n_frames] if batch.get("mels") is not None else self.input_mels(audios, n_frames)
+        y_g_hat = self.generator(mels, pitches, **gen_kw)
+        y_g_hat_mel = self.input_mels(y_g_hat, n_frames)
+        mask = (torch.arange(mels.shape[2], device=mels.device)[None, :] < mel_lens[:, None])[:, None].float()
+        return float(F.l1_loss(mels * mask, y_g_hat_mel * mask))
 
     def on_train_epoch_end(self):
         """train.py:225-231: both exponential schedules step once per epoch."""

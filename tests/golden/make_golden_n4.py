@@ -53,6 +53,8 @@ class FakeLightningModule(torch.nn.Module):
         super().__init__()
         self.logged = {}
         self.trainer = types.SimpleNamespace(is_last_batch=False)
+        self.logger = None
+        self.global_step = 0
         self._opt = None
 
     def _conf(self):
@@ -79,7 +81,7 @@ class Cfg(dict):
 
 def load_reference_trainer():
     ref = mg.load_reference()
-    _stub("matplotlib"); _stub("matplotlib.pyplot")
+    _stub("matplotlib"); _stub("matplotlib.pyplot", close=lambda *a, **k: None)
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     pl = _stub("pytorch_lightning", LightningModule=FakeLightningModule, Trainer=_Any(), seed_everything=lambda *a, **k: None)
     _stub("pytorch_lightning.loggers", TensorBoardLogger=type("TensorBoardLogger", (), {}), WandbLogger=type("WandbLogger", (), {}))
@@ -125,6 +127,12 @@ def main():
     calls = []
     mod.generator.register_forward_hook(lambda m, a, o: calls.append(o.detach().clone()))
     out = {}
+    # validation_step (train.py:241-270) first, on the initial weights; its plotting / logging tail runs on stubs
+    with mg.RecordedRandom(nu.SEED_DRAWS + 2), torch.no_grad():
+        mod.validation_step(batch, 0)
+    out["log_valid_loss"] = np.float64(mod.logged["valid_loss"])
+    out["valid_wav"] = calls[-1].numpy()
+    calls.clear()
     with mg.RecordedRandom(nu.SEED_DRAWS) as rr:
         mod.training_step(batch, 0)
     print("draws:", [(k, a.shape) for k, a in rr.log])

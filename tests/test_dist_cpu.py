@@ -70,3 +70,34 @@ def test_grad_sync_buckets_average_over_ranks_gloo():
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_sync_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def _voc_sync_worker(rank, world, port, ret):
+    """vocoder_gan.average_gradients (the DDP role of the vocoder trainer, configs/vocoder_nsf_hifigan.py:25) on gloo/CPU:
+    per-network averaging, parameters without a gradient are left alone."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from fish_diffusion_b200.vocoder_gan import DiscriminatorP, average_gradients
+    torch.manual_seed(0)                                         # same weights on every rank
+    d = DiscriminatorP(3)
+    x = torch.randn(2, 1, 300, generator=torch.Generator().manual_seed(100 + rank))    # different data per rank
+    out, _ = d(x)
+    out.square().mean().backward()
+    local = [p.grad.clone() for p in d.parameters()]
+    extra = torch.nn.Parameter(torch.ones(3))                    # never used: no gradient, must stay None
+    average_gradients(list(d.parameters()) + [extra])
+    gathered = [None] * world
+    torch.distributed.all_gather_object(gathered, [g.numpy() for g in local])
+    want = [sum(torch.from_numpy(gathered[r][i]) for r in range(world)) / world for i in range(len(local))]
+    ok = all(torch.allclose(p.grad, w, rtol=1e-6, atol=1e-8) for p, w in zip(d.parameters(), want)) and extra.grad is None
+    ret[rank] = bool(ok)
+    torch.distributed.destroy_process_group()
+
+
+def test_vocoder_trainer_gradient_average_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_voc_sync_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))

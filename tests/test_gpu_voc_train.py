@@ -174,6 +174,11 @@ def test_training_step_vs_reference_golden(golden):
     print(f"input log-mel: max |native - reference| = {e_mel:.2e}")
     assert mels.shape == g["mels"].shape and e_mel < 2e-3
     B, S = batch["audio"].shape[0], batch["audio"].shape[2]
+    # validation_step (train.py:241-270) on the initial weights: inference kernels + native mels against the logged loss
+    vri, vnz = _draws(nu.SEED_DRAWS + 2, [(B, 9), (B, S, 9)])
+    v = tr.validation_step(batch, rand_ini=vri, sine_noise=vnz)
+    print(f"valid_loss {v:.6f} vs reference {float(g['log_valid_loss']):.6f}")
+    assert abs(v - float(g["log_valid_loss"])) < 1e-3 * float(g["log_valid_loss"])
     ri, nz = _draws(nu.SEED_DRAWS, [(B, 9), (B, S, 9)])
     # the golden is the reference in full float32: keep cuDNN (the discriminators) out of TF32 for this comparison
     tf32 = torch.backends.cudnn.allow_tf32
