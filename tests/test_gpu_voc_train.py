@@ -132,11 +132,13 @@ def _draws(seed, shapes):
 
 
 @pytest.mark.parametrize("name,precision,wav_tol,worst_tol,median_tol", [
-    ("n4_gen_init", "f16", 2e-5, 5e-3, 2e-4), ("n4_gen_init", "f16x1", 3e-2, 1.0, 0.2), ("n4_gen", "f16", 3e-4, 5e-2, 1.5e-2)])
+    ("n4_gen_init", "f16", 5e-6, 2e-3, 5e-5), ("n4_gen_init", "f16x1", 3e-3, 0.5, 0.1), ("n4_gen", "f16", 3e-4, 5e-2, 1.5e-2)])
 def test_generator_gradients_vs_reference_golden(golden, name, precision, wav_tol, worst_tol, median_tol):
     """The CUDA path against the float64 reference Generator (autograd, smooth loss).
       n4_gen_init  the reference's own initialisation: well conditioned (reference float32 vs float64: 7e-8 on the audio,
-                   3.6e-6 worst gradient, single LeakyReLU mask flips aside: 5e-4 on one conv) -- the tight pin;
+                   3.6e-6 worst gradient, single LeakyReLU mask flips aside: 5e-4 on one conv) -- the tight pin.  Measured
+                   on a B200 (profiles/r02i_n4_gpu_tests.log): three products 3.7e-7 on the audio, worst gradient 6.8e-6,
+                   median 1.7e-6; one product 6.9e-5 / 7.2e-2 / 2.0e-2;
       n4_gen       3x those weights: saturated output, chaotic gradient; the reference's own float32 runs sit at worst
                    9.9e-3 / median 2.6e-3 (8 threads) from the arbiter (stored in the golden); measured here on a B200:
                    audio 5.9e-5, worst 1.6e-2, median 5.7e-3.  One-product arithmetic is not compared there."""
