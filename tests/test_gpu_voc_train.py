@@ -180,7 +180,7 @@ def test_training_step_vs_reference_golden(golden):
     vri, vnz = _draws(nu.SEED_DRAWS + 2, [(B, 9), (B, S, 9)])
     v = tr.validation_step(batch, rand_ini=vri, sine_noise=vnz)
     print(f"valid_loss {v:.6f} vs reference {float(g['log_valid_loss']):.6f}")
-    assert abs(v - float(g["log_valid_loss"])) < 1e-3 * float(g["log_valid_loss"])
+    assert abs(v - float(g["log_valid_loss"])) < 1e-4 * float(g["log_valid_loss"])          # measured 1.6e-6
     ri, nz = _draws(nu.SEED_DRAWS, [(B, 9), (B, S, 9)])
     # the golden is the reference in full float32: keep cuDNN (the discriminators) out of TF32 for this comparison
     tf32 = torch.backends.cudnn.allow_tf32
@@ -190,9 +190,10 @@ def test_training_step_vs_reference_golden(golden):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     print(out)
-    assert abs(out["loss_disc"] - float(g["log_train_loss_disc"])) < 2e-3 * float(g["log_train_loss_disc"])
-    assert abs(out["loss_gen"] - float(g["log_train_loss_gen"])) < 2e-3 * float(g["log_train_loss_gen"])
-    assert abs(out["envelope"] - float(g["log_train_loss_g_envelope"])) < 1e-3
+    # measured on a B200: 5.7e-7, 6.6e-6, 1e-7 (profiles/r02i_n4_gpu_tests.log)
+    assert abs(out["loss_disc"] - float(g["log_train_loss_disc"])) < 1e-4 * float(g["log_train_loss_disc"])
+    assert abs(out["loss_gen"] - float(g["log_train_loss_gen"])) < 1e-4 * float(g["log_train_loss_gen"])
+    assert abs(out["envelope"] - float(g["log_train_loss_g_envelope"])) < 1e-4
     for prefix, sub in (("generator", tr.generator), ("mpd", tr.mpd), ("msd", tr.msd)):
         nu.check_gradients(g, [(n, p.grad.cpu().numpy()) for n, p in sub.named_parameters()], f"grad_{prefix}.", 0.5, 0.1,
                            f"training-step gradients of {prefix} (CUDA) vs reference")
