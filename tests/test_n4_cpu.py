@@ -226,6 +226,21 @@ def test_discriminators_and_losses_match_reference_bit_for_bit():
         assert float(G.generator_loss(a[1])[0]) == float(ref.nsf.generator_loss(b[1])[0])
 
 
+def test_trainer_state_dict_layout():
+    """`generator.*`, `mpd.*`, `msd.*` and nothing else: the loss-side mel transforms are not registered (the reference keeps
+    them in a plain list, train.py:55-75), so the three networks of a reference Lightning checkpoint map key for key."""
+    from fish_diffusion_b200.vocoder_gan import HifiGanTrainer
+    tr = HifiGanTrainer(nu.train_config())
+    keys = list(tr.state_dict().keys())
+    assert all(k.split(".")[0] in ("generator", "mpd", "msd") for k in keys)
+    assert {k[len("generator."):] for k in keys if k.startswith("generator.")} == set(_load_ckpt_generator().keys())
+    assert len(tr.mpd.discriminators) == 2 and len(tr.msd.discriminators) == 3
+    opts, scheds = tr.configure_optimizers()
+    assert opts[0].defaults["lr"] == 0.0002 and opts[0].defaults["betas"] == (0.8, 0.99) and scheds[0].gamma == 0.999
+    n_g = sum(p.numel() for g in opts[0].param_groups for p in g["params"])
+    assert n_g == sum(p.numel() for p in tr.generator.parameters())
+
+
 def test_training_nodes_refuse_cpu_tensors():
     """No CPU path: without the emulation the nodes raise on CPU tensors."""
     from fish_diffusion_b200 import Generator, _native
