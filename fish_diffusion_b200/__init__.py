@@ -19,5 +19,6 @@ from . import formats  # noqa: F401
 from .vocoder_gan import (HifiGanTrainer, MultiPeriodDiscriminator, MultiScaleDiscriminator,  # noqa: F401
                           average_gradients)
 from .vocoder_train import generator_forward_train  # noqa: F401
+from .trainers import DiffSingerTrainer, WarmupCosine, ema_update  # noqa: F401
 
 __version__ = "0.1.0"
