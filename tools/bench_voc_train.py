@@ -60,6 +60,15 @@ def measure(a):
     gen = Generator(h).to(dev)
     gen_flops_fwd = 614.9e6 * B * T            # 614.9 MFLOP per mel frame (hop 256)
     out = {"config": "config_v1_256.json", "batch": B, "frames": T, "samples": S, "steps": a.steps}
+    peak, peak_src = 1400.0, "fallback (B200_PROFILING.md)"
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            d = json.load(f)
+        peak, peak_src = d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json), sustained bf16"
+    out["roofline_note"] = {"bound": "tensor", "peak": peak, "unit": "TFLOP/s", "peak_source": peak_src,
+                            "algorithmic_flops_per_step": 3 * gen_flops_fwd,
+                            "what": "generator forward + backward = 3 x the forward's 614.9 MFLOP per mel frame (SURVEY 8d)"}
 
     def native_step(cfg):
         for p in gen.parameters():
@@ -74,8 +83,9 @@ def measure(a):
             native_step(cfg)
             launches = N.launch_count() - l0
             ms = timed(lambda: native_step(cfg), a.steps)
-            out[f"native_gen_fwd_bwd_{prec}"] = {"ms": ms, "launches_per_step": launches,
-                                                 "algorithmic_tflops": 3 * gen_flops_fwd / ms / 1e9}
+            tfl = 3 * gen_flops_fwd / ms / 1e9
+            out[f"native_gen_fwd_bwd_{prec}"] = {"ms": ms, "launches_per_step": launches, "algorithmic_tflops": tfl,
+                                                 "frac_of_peak_algorithmic": tfl / peak}
         except Exception as e:  # noqa: BLE001
             out[f"native_gen_fwd_bwd_{prec}"] = {"error": repr(e)[:300]}
 
