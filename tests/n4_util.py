@@ -93,16 +93,3 @@ def check_gradients(g, named_grads, prefix, worst_tol, median_tol, what):
     assert worst[0] < worst_tol, f"{what}: worst gradient error {worst[0]:.2e} ({worst[1]}) >= {worst_tol:.1e}"
     assert median[0] < median_tol, f"{what}: median gradient error {median[0]:.2e} >= {median_tol:.1e}"
     return worst[0], median[0]
-
-
-def check_summary(g, key, arr, tol, what=""):
-    """-> (norm error, sampled-entry error) of `arr` against the stored summary, both relative to the stored norm."""
-    a = np.asarray(arr, dtype=np.float64).reshape(-1)
-    n_ref = float(g[key + "_norm"])
-    idx, val = g[key + "_idx"], g[key + "_val"].astype(np.float64)
-    scale = max(n_ref, 1e-30)
-    e_norm = abs(np.linalg.norm(a) - n_ref) / scale
-    # sampled entries: compare as a vector, normalised by the expected magnitude of `samples` entries of the tensor
-    e_val = np.linalg.norm(a[idx] - val) / max(np.linalg.norm(val), scale * np.sqrt(len(idx) / a.size), 1e-30)
-    assert e_norm < tol and e_val < tol, f"{what}{key}: norm err {e_norm:.2e}, sample err {e_val:.2e} (tol {tol:.1e})"
-    return e_norm, e_val
