@@ -251,3 +251,21 @@ def test_training_nodes_refuse_cpu_tensors():
     with pytest.raises(_native.NativeError):
         VT.ResBlock1Fn.apply(VT.TrainCfg(), (1,), torch.zeros(1, 8, 8), torch.zeros(8, 8, 3), torch.zeros(8),
                              torch.zeros(8, 8, 3), torch.zeros(8))
+
+
+def test_generator_forward_train_argument_checks():
+    """Loud errors of the differentiable generator (host logic): ResBlock2 generators have no native backward, and a
+    config whose hop_size disagrees with its upsample rates is refused (models.py:411 relies on their equality)."""
+    from fish_diffusion_b200 import Generator
+    from fish_diffusion_b200 import vocoder_train as VT
+    h = nu.train_config()
+    mel, f0 = torch.zeros(1, 32, 4), torch.full((1, 4), 200.0)
+    with emulated_native():
+        gen2 = Generator(dict(h, resblock="2", resblock_dilation_sizes=[[1, 3]] * 3))
+        with pytest.raises(NotImplementedError):
+            VT.generator_forward_train(gen2, mel, f0)
+        bad = Generator(dict(h, hop_size=128))
+        with pytest.raises(ValueError):
+            VT.generator_forward_train(bad, mel, f0)
+        wav = VT.generator_forward_train(Generator(h), mel, f0[:, None])          # [B,1,T] pitches as the data loader gives
+        assert wav.shape == (1, 1, 4 * 64) and wav.requires_grad
