@@ -101,3 +101,48 @@ def test_vocoder_trainer_gradient_average_gloo():
     port = 33500 + (os.getpid() % 2000)
     mp.spawn(_voc_sync_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def _voc_step_worker(rank, world, port, ret):
+    """One whole HifiGanTrainer.training_step per rank on different data with the gradient-averaging hook (gloo): the
+    replicas stay identical.  Device primitives are emulated (tests/native_emu.py) -- this checks the host-side data-parallel
+    plumbing of the vocoder trainer, the role of DDPStrategy in configs/vocoder_nsf_hifigan.py:25."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    import n4_util as nu
+    from native_emu import emulated_native
+    from fish_diffusion_b200.vocoder_gan import HifiGanTrainer, average_gradients
+    h = dict(nu.train_config(), discriminator_periods=[2])
+    tr = HifiGanTrainer(h, precision="f16")
+    sd = torch.load(os.path.join(here, "golden", "ref_generator_small.ckpt"), map_location="cpu")["generator"]
+    tr.generator.load_state_dict({k: v / 3 for k, v in sd.items()})
+    nu.fill_discriminators(tr.mpd, tr.msd)
+    tr.train()
+    batch = nu.make_batch()
+    S = 4096                                                     # the 4096-point loss mel needs more than 2048 samples
+    batch = dict(pitches=batch["pitches"][rank:rank + 1, :, :S // 64], audio=batch["audio"][rank:rank + 1, :, :S],
+                 audio_lens=torch.tensor([S]))
+    mel = torch.randn(1, 32, S // 64, generator=torch.Generator().manual_seed(7 + rank)) - 2.0
+    batch["mels"] = mel
+    with emulated_native():
+        out = tr.training_step(batch, reduce_grads=average_gradients)
+    digest = torch.cat([p.detach().double().reshape(-1)[:64] for p in tr.parameters()])
+    gathered = [None] * world
+    torch.distributed.all_gather_object(gathered, (digest.numpy(), out["loss_gen"]))
+    same = all(float(abs(gathered[0][0] - g[0]).max()) == 0.0 for g in gathered)
+    ret[rank] = (bool(same), gathered[0][1] != gathered[1][1])    # identical replicas, different local losses
+    torch.distributed.destroy_process_group()
+
+
+def test_vocoder_training_step_two_ranks_stay_identical_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_voc_step_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world)), dict(ret)
+    assert all(ret[r][1] for r in range(world))
