@@ -72,7 +72,10 @@ def test_product_does_not_import_oracle():
         for fn in files:
             if fn.endswith(".py"):
                 with open(os.path.join(dirpath, fn)) as f:
-                    assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read(), flags=re.M), fn
+                    src = f.read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                    # nor the test-only emulation of the device primitives (tests/native_emu.py), nor anything under tests/
+                    assert not re.search(r"^\s*(from|import)\s+(native_emu|n4_util|tests)\b", src, flags=re.M), fn
 
 
 def test_precision_codes_and_wgrad_shape_rule():
